@@ -1,0 +1,155 @@
+/* spx.h -- C ABI of libspx: the B200-native spectral hot path of sdr-iq-visualizer.
+ *
+ * The reference (JaredWinkens/sdr-iq-visualizer) is pure Python and has no FFI of its own; its
+ * boundary for this path is a set of Python call sites.  Each entry
+ * point below names the reference lines it replaces.  The Python host layer
+ * (sdr_iq_visualizer_b200/_native.py) binds exactly these symbols with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status: SPX_OK (0) or a negative SPX_E_* code; the message
+ *     is available from spx_last_error() (thread-local).  No C++ exception crosses the boundary.
+ *   - the caller owns every input and output buffer; a plan owns only scratch/staging memory.
+ *   - `mem` says where the caller's buffers live: SPX_MEM_HOST (the library stages them through
+ *     pinned memory with pipelined cudaMemcpyAsync) or SPX_MEM_DEVICE (pointers are used as is on
+ *     `stream`; nothing is synchronised).
+ *   - spectra are in fftshift order: index j <-> bin (j + N/2) mod N, freqs[j] = (j - N/2) fs/N + fc
+ *     (reference app/sdr/streamer.py:119-120).
+ *   - one plan may be used by one thread at a time (calls on the same plan are serialised by an
+ *     internal mutex); different plans are independent.
+ */
+#ifndef SPX_H_
+#define SPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SPX_API __attribute__((visibility("default")))
+#else
+#define SPX_API
+#endif
+
+/* status codes */
+#define SPX_OK 0
+#define SPX_E_INVALID (-1)     /* bad argument */
+#define SPX_E_CUDA (-2)        /* CUDA runtime / launch failure */
+#define SPX_E_NOMEM (-3)       /* allocation failed */
+#define SPX_E_UNSUPPORTED (-4) /* e.g. nfft not a power of two in [16, 1048576] */
+#define SPX_E_NODEVICE (-5)    /* no CUDA device: there is NO CPU fallback */
+
+/* enums */
+#define SPX_WINDOW_RECT 0     /* streamer.py:119 (no window) */
+#define SPX_WINDOW_HANN 1     /* np.hanning: mlab default behind process_sigmf_data.py:188 */
+#define SPX_WINDOW_BLACKMAN 2 /* np.blackman */
+#define SPX_FMT_CF32 0        /* complex64 (SigMF cf32_le; callbacks.py:307-310) */
+#define SPX_FMT_CI16 1        /* interleaved int16 I,Q (Pluto iio buffer; SigMF ci16_le) */
+#define SPX_MEM_HOST 0
+#define SPX_MEM_DEVICE 1
+
+SPX_API int spx_abi_version(void);
+/* thread-local message of the last failing call on this thread ("" if none) */
+SPX_API const char* spx_last_error(void);
+
+SPX_API int spx_device_count(int* count);
+
+typedef struct {
+    uint32_t struct_size;
+    int32_t sm_count;
+    int32_t cc_major, cc_minor;
+    int32_t l2_bytes;
+    int32_t max_smem_optin;
+    int64_t total_mem;
+    char name[64];
+} spx_device_info;
+SPX_API int spx_get_device_info(int device, spx_device_info* out);
+
+/* F = (n_samples - nfft) / hop + 1 (0 if n_samples < nfft): frame slicing of SURVEY.md A2
+ * (one rx buffer = one frame at streamer.py:114-119; mlab framing behind process_sigmf_data.py:188) */
+SPX_API int64_t spx_frame_count(int64_t n_samples, int32_t nfft, int32_t hop);
+
+/* ---------------------------------------------------------------- pinned host memory */
+SPX_API int spx_host_alloc(void** out, size_t bytes);
+SPX_API int spx_host_free(void* p);
+SPX_API int spx_host_register(void* p, size_t bytes);
+SPX_API int spx_host_unregister(void* p);
+
+/* ---------------------------------------------------------------- device memory (for callers
+ * that keep data resident, e.g. bench.py's device-timed leg and the multi-GPU sharder) */
+SPX_API int spx_device_alloc(int device, void** out, size_t bytes);
+SPX_API int spx_device_free(int device, void* p);
+SPX_API int spx_memcpy_h2d(int device, void* dst, const void* src, size_t bytes);
+SPX_API int spx_memcpy_d2h(int device, void* dst, const void* src, size_t bytes);
+SPX_API int spx_memset(int device, void* dst, int value, size_t bytes);
+SPX_API int spx_device_sync(int device);
+
+/* ---------------------------------------------------------------- STFT plan */
+typedef struct spx_plan spx_plan;
+
+typedef struct {
+    uint32_t struct_size; /* sizeof(spx_plan_config) */
+    int32_t device;
+    int32_t nfft;     /* power of two, 16 .. 1048576 */
+    int32_t hop;      /* 1 .. nfft (nfft = no overlap, nfft/4 = 75 % overlap) */
+    int32_t window;   /* SPX_WINDOW_* */
+    int32_t in_fmt;   /* SPX_FMT_* */
+    float in_scale;   /* multiplies every sample: 1.0 stream path, 2^-15 SigMF ci16_le */
+    float db_eps;     /* dB rows are 20*log10(|X| + db_eps); reference 1e-12 (streamer.py:121) */
+    int32_t variant;  /* kernel tuning variant, 0 = default */
+    int32_t reserved;
+} spx_plan_config;
+
+SPX_API int spx_plan_create(spx_plan** out, const spx_plan_config* cfg);
+SPX_API int spx_plan_destroy(spx_plan* plan);
+/* wait for everything the plan has enqueued on its own streams */
+SPX_API int spx_plan_sync(spx_plan* plan);
+
+typedef struct {
+    uint32_t struct_size; /* sizeof(spx_stft_args) */
+    int32_t mem;          /* SPX_MEM_HOST or SPX_MEM_DEVICE, applies to every pointer below */
+    const void* in;       /* n_streams streams of n_samples samples, stream s starts at s*stream_stride */
+    int64_t n_samples;    /* per stream */
+    int64_t stream_stride;/* in samples; ignored when n_streams == 1 */
+    int32_t n_streams;    /* >= 1 */
+    int32_t accumulate;   /* 0: welch_acc/maxhold are overwritten; 1: accumulated into (+=, max=) */
+    /* outputs, each optional (NULL = not wanted); F = spx_frame_count(n_samples, nfft, hop) */
+    float* db_rows;       /* [n_streams*F][nfft]  20*log10(|X|+eps), fftshift order (streamer.py:121) */
+    uint8_t* wf_rows;     /* [n_streams*F][nfft]  clip(floor((db-vmin)*256/(vmax-vmin)),0,255) (A7) */
+    float* spec_rows;     /* [n_streams*F][nfft][2] complex spectrum, fftshift order (streamer.py:119) */
+    double* welch_acc;    /* [n_streams][nfft]    sum over frames of |X|^2 (A8; mlab.psd numerator) */
+    float* maxhold;       /* [n_streams][nfft]    max over frames of |X|^2 (A8) */
+    float vmin, vmax;     /* waterfall colour range in dB */
+    void* stream;         /* cudaStream_t for SPX_MEM_DEVICE (NULL = the plan's compute stream) */
+    int64_t n_frames_out; /* out: F */
+    int64_t h2d_bytes_out;/* out: bytes copied host->device by this call (SPX_MEM_HOST) */
+    int64_t d2h_bytes_out;/* out: bytes copied device->host by this call */
+} spx_stft_args;
+
+/* windowed STFT -> PSD -> waterfall; replaces streamer.py:119-121 (per buffer) and the frame loop of
+ * mlab.psd behind process_sigmf_data.py:188, batched over all frames of the input. */
+SPX_API int spx_stft_exec(spx_plan* plan, spx_stft_args* args);
+
+/* Measurement helper: runs spx_stft_exec (SPX_MEM_DEVICE buffers only) warmup+iters times on the
+ * launch stream, each bracketed by CUDA events; optionally writes a 256 MiB buffer before every
+ * iteration to flush the 126 MB L2.  ms_each[iters] receives the device time of each timed launch. */
+SPX_API int spx_stft_time(spx_plan* plan, spx_stft_args* args, int32_t warmup, int32_t iters, int32_t flush_l2,
+                          float* ms_each);
+
+/* Welch density from the accumulated numerator: Pxx[k] = acc[k] / (n_frames * fs * sum(w^2))
+ * (mlab.psd, two-sided) and 10*log10 of it.  Either output may be NULL.  `mem` as above. */
+SPX_API int spx_welch_finalize(spx_plan* plan, int32_t mem, const double* welch_acc, int64_t n_frames, double fs,
+                       double* pxx, double* pxx_db, void* stream);
+
+/* sum(w^2) and sum(w) of the plan's float64 window (in_scale is applied to the data, not counted here) */
+SPX_API int spx_plan_window_sums(spx_plan* plan, double* sum_w2, double* sum_w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPX_H_ */

@@ -1,0 +1,261 @@
+"""ctypes binding of libspx (include/spx.h) -- the only door from Python to the CUDA kernels.
+
+There is no CPU fallback: if the shared library cannot be loaded, or no CUDA device is present,
+every compute entry point raises :class:`SpectralError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libspx.so")
+
+OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_NODEVICE = 0, -1, -2, -3, -4, -5
+WINDOW_RECT, WINDOW_HANN, WINDOW_BLACKMAN = 0, 1, 2
+FMT_CF32, FMT_CI16 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class SpectralError(RuntimeError):
+    """A libspx call failed (CUDA fault, bad argument, no device ...).  Deliberately NOT an OSError:
+    the reference streamer treats OSError/Exception inside its read loop as a radio fault
+    (/root/reference/app/sdr/streamer.py:134-174); callers can tell this one apart."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libspx error {code}: {message}")
+        self.code = code
+
+
+class spx_device_info(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
+                ("l2_bytes", C.c_int32), ("max_smem_optin", C.c_int32), ("total_mem", C.c_int64), ("name", C.c_char * 64)]
+
+
+class spx_plan_config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("nfft", C.c_int32), ("hop", C.c_int32),
+                ("window", C.c_int32), ("in_fmt", C.c_int32), ("in_scale", C.c_float), ("db_eps", C.c_float),
+                ("variant", C.c_int32), ("reserved", C.c_int32)]
+
+
+class spx_stft_args(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("in_", C.c_void_p), ("n_samples", C.c_int64),
+                ("stream_stride", C.c_int64), ("n_streams", C.c_int32), ("accumulate", C.c_int32),
+                ("db_rows", C.c_void_p), ("wf_rows", C.c_void_p), ("spec_rows", C.c_void_p),
+                ("welch_acc", C.c_void_p), ("maxhold", C.c_void_p), ("vmin", C.c_float), ("vmax", C.c_float),
+                ("stream", C.c_void_p), ("n_frames_out", C.c_int64), ("h2d_bytes_out", C.c_int64),
+                ("d2h_bytes_out", C.c_int64)]
+
+
+# name -> (restype, argtypes); must list every symbol include/spx.h declares (tests check this)
+_SIGNATURES = {
+    "spx_abi_version": (C.c_int, []),
+    "spx_last_error": (C.c_char_p, []),
+    "spx_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "spx_get_device_info": (C.c_int, [C.c_int, C.POINTER(spx_device_info)]),
+    "spx_frame_count": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "spx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "spx_host_free": (C.c_int, [C.c_void_p]),
+    "spx_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "spx_host_unregister": (C.c_int, [C.c_void_p]),
+    "spx_device_alloc": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
+    "spx_device_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "spx_memcpy_h2d": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "spx_memcpy_d2h": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "spx_memset": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_size_t]),
+    "spx_device_sync": (C.c_int, [C.c_int]),
+    "spx_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(spx_plan_config)]),
+    "spx_plan_destroy": (C.c_int, [C.c_void_p]),
+    "spx_plan_sync": (C.c_int, [C.c_void_p]),
+    "spx_stft_exec": (C.c_int, [C.c_void_p, C.POINTER(spx_stft_args)]),
+    "spx_stft_time": (C.c_int, [C.c_void_p, C.POINTER(spx_stft_args), C.c_int32, C.c_int32, C.c_int32,
+                                C.POINTER(C.c_float)]),
+    "spx_welch_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "spx_plan_window_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu into csrc/libspx.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        raise SpectralError(E_UNSUPPORTED, "nvcc not found: cannot build libspx.so")
+    env = dict(os.environ)
+    if shutil.which("nvcc") is None:
+        env["PATH"] = "/usr/local/cuda/bin:" + env.get("PATH", "")
+    jobs = str(max(1, min(8, os.cpu_count() or 1)))
+    res = subprocess.run(["make", "-C", CSRC, "-j", jobs], env=env, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0 or not os.path.exists(LIB_PATH):
+        raise SpectralError(E_UNSUPPORTED, "building libspx.so failed:\n" + res.stderr[-2000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load (building on first use if the .so is absent) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            build()
+        try:
+            handle = C.CDLL(LIB_PATH)
+        except OSError as e:  # missing extension is fatal: no fallback path exists
+            raise SpectralError(E_UNSUPPORTED, f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().spx_last_error() or b"").decode(errors="replace")
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise SpectralError(rc, last_error())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().spx_device_count(C.byref(n))
+    if rc == E_NODEVICE:
+        return 0
+    check(rc)
+    return int(n.value)
+
+
+def require_device() -> int:
+    n = device_count()
+    if n == 0:
+        raise SpectralError(E_NODEVICE, "no CUDA device available; this package has no CPU fallback")
+    return n
+
+
+def device_info(device: int = 0) -> dict:
+    info = spx_device_info()
+    check(lib().spx_get_device_info(device, C.byref(info)))
+    return {"name": info.name.decode(), "sm_count": info.sm_count, "cc": (info.cc_major, info.cc_minor),
+            "l2_bytes": info.l2_bytes, "max_smem_optin": info.max_smem_optin, "total_mem": info.total_mem}
+
+
+def frame_count(n_samples: int, nfft: int, hop: int) -> int:
+    return int(lib().spx_frame_count(int(n_samples), int(nfft), int(hop)))
+
+
+# ----------------------------------------------------------------------------- memory helpers
+class _Pinned:
+    """Owner of one cudaHostAlloc block, exposed to numpy through __array_interface__."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(lib().spx_host_alloc(C.byref(p), nbytes))
+        self.ptr = p.value
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.spx_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array backed by page-locked host memory (cudaHostAlloc): makes the H2D/D2H legs of
+    SPX_MEM_HOST execution truly asynchronous.  The block is freed when the last view dies."""
+    dtype = np.dtype(dtype)
+    shape = tuple(int(v) for v in (shape if np.ndim(shape) else (shape,)))
+    n = int(np.prod(shape))
+    nbytes = max(1, n * dtype.itemsize)
+    raw = np.asarray(_Pinned(nbytes))
+    return raw[: n * dtype.itemsize].view(dtype).reshape(shape)
+
+
+class DeviceArray:
+    """A typed device allocation owned by Python (cudaMalloc through libspx)."""
+
+    def __init__(self, shape, dtype, device: int = 0, zero: bool = False):
+        self.shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.device = int(device)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib().spx_device_alloc(self.device, C.byref(p), max(1, self.nbytes)))
+        self.ptr = p.value
+        if zero:
+            self.zero_()
+
+    @classmethod
+    def from_host(cls, arr: np.ndarray, device: int = 0) -> "DeviceArray":
+        arr = np.ascontiguousarray(arr)
+        d = cls(arr.shape, arr.dtype, device)
+        d.copy_from_host(arr)
+        return d
+
+    def copy_from_host(self, arr: np.ndarray) -> None:
+        arr = np.ascontiguousarray(arr)
+        if arr.nbytes != self.nbytes:
+            raise ValueError("size mismatch")
+        check(lib().spx_memcpy_h2d(self.device, self.ptr, arr.ctypes.data, self.nbytes))
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        if self.nbytes:
+            check(lib().spx_memcpy_d2h(self.device, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def zero_(self) -> None:
+        check(lib().spx_memset(self.device, self.ptr, 0, self.nbytes))
+
+    def free(self) -> None:
+        if getattr(self, "ptr", None):
+            try:
+                lib().spx_device_free(self.device, self.ptr)
+            finally:
+                self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def device_sync(device: int = 0) -> None:
+    check(lib().spx_device_sync(device))
+
+
+def as_ptr(x) -> tuple:
+    """(pointer, mem) of a numpy array, DeviceArray, torch tensor or None."""
+    if x is None:
+        return None, None
+    if isinstance(x, DeviceArray):
+        return x.ptr, MEM_DEVICE
+    if isinstance(x, np.ndarray):
+        if not x.flags.c_contiguous:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data, MEM_HOST
+    if hasattr(x, "data_ptr") and hasattr(x, "is_cuda"):  # torch tensor (plumbing only)
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return int(x.data_ptr()), (MEM_DEVICE if x.is_cuda else MEM_HOST)
+    raise TypeError(f"unsupported buffer type {type(x)!r}")

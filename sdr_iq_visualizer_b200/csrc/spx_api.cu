@@ -1,0 +1,491 @@
+// spx_api.cu -- the C ABI of libspx (include/spx.h): plans, device/host execution, staging.
+//
+// Host-memory execution (SPX_MEM_HOST) is a three-stream pipeline: pieces of the input go
+// host->device on `s_h2d`, every piece releases the frames it completes to the fused kernel on
+// `s_compute`, and finished rows drain device->host on `s_d2h`; all three overlap when the
+// caller's buffers are pinned (spx_host_alloc / spx_host_register).  This is the new
+// "pinned, double-buffered" ingest of SURVEY.md section 0 (the reference queues one dict per
+// rx buffer: /root/reference/app/sdr/streamer.py:123-131,186-194).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "spx_plan.h"
+#include "spx_stft_kernel.cuh"
+#include "spx_tables.h"
+
+namespace spx {
+
+static thread_local char g_err[512] = "";
+
+int spx_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return SPX_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        return spx_set_error(SPX_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return SPX_OK;
+}
+void DevBuf::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+int plan_event(spx_plan* pl, size_t i, cudaEvent_t* out) {
+    while (pl->events.size() <= i) {
+        cudaEvent_t e;
+        SPX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        pl->events.push_back(e);
+    }
+    *out = pl->events[i];
+    return SPX_OK;
+}
+
+// ------------------------------------------------------------------ dispatch
+int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long long stream_stride, long long frames,
+                       float* db_rows, unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold,
+                       float vmin, float vmax, cudaStream_t st) {
+    if (frames <= 0 || n_streams <= 0) return SPX_OK;
+    StftLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.p.in = in;
+    L.p.stream_stride = stream_stride;
+    L.p.frames_per_stream = frames;
+    L.p.n_streams = (int)n_streams;
+    L.p.hop = pl->cfg.hop;
+    L.p.win = pl->d_win;
+    L.p.tw = pl->d_tw;
+    L.p.db_rows = db_rows;
+    L.p.wf_rows = wf_rows;
+    L.p.spec_rows = spec_rows;
+    L.p.welch_acc = welch_acc;
+    L.p.maxhold = maxhold;
+    L.p.db_eps = pl->cfg.db_eps;
+    L.p.q_vmin = vmin;
+    L.p.q_scale = 256.0f / (vmax - vmin);
+    L.nfft = pl->cfg.nfft;
+    L.in_fmt = pl->cfg.in_fmt;
+    L.variant = pl->cfg.variant;
+    L.sm_count = pl->sm_count;
+    L.total_frames = frames * n_streams;
+    L.stream = st;
+    const int n = pl->cfg.nfft;
+    if (n <= 512) return launch_stft_small(L);
+    if (n <= 2048) return launch_stft_1k2k(L);
+    if (n == 4096) return launch_stft_4k(L);
+    if (n == 8192) return launch_stft_8k(L);
+    return spx_set_error(SPX_E_UNSUPPORTED, "nfft %d: large-N path not built yet", n);
+}
+
+static size_t in_elt(const spx_plan* pl) { return pl->cfg.in_fmt == SPX_FMT_CI16 ? 4 : 8; }
+
+// ------------------------------------------------------------------ host-memory pipeline
+static int stft_exec_host(spx_plan* pl, spx_stft_args* a, long long F) {
+    const int N = pl->cfg.nfft, hop = pl->cfg.hop;
+    const size_t elt = in_elt(pl);
+    const long long S = a->n_streams, L = a->n_samples;
+    const long long stride_host = S > 1 ? a->stream_stride : 0;
+    const size_t rows = (size_t)(S * F);
+    SPX_TRY(pl->st_in.reserve((size_t)(S * L) * elt));
+    if (a->db_rows) SPX_TRY(pl->st_db.reserve(rows * N * sizeof(float)));
+    if (a->wf_rows) SPX_TRY(pl->st_wf.reserve(rows * N));
+    if (a->spec_rows) SPX_TRY(pl->st_spec.reserve(rows * N * sizeof(float2)));
+    if (a->welch_acc) SPX_TRY(pl->st_welch.reserve((size_t)S * N * sizeof(double)));
+    if (a->maxhold) SPX_TRY(pl->st_max.reserve((size_t)S * N * sizeof(float)));
+    char* d_in = (char*)pl->st_in.ptr;
+    float* d_db = a->db_rows ? (float*)pl->st_db.ptr : nullptr;
+    unsigned char* d_wf = a->wf_rows ? (unsigned char*)pl->st_wf.ptr : nullptr;
+    float2* d_spec = a->spec_rows ? (float2*)pl->st_spec.ptr : nullptr;
+    double* d_welch = a->welch_acc ? (double*)pl->st_welch.ptr : nullptr;
+    float* d_max = a->maxhold ? (float*)pl->st_max.ptr : nullptr;
+    long long h2d = 0, d2h = 0;
+
+    // accumulators: start from zero or from the caller's running values
+    if (d_welch) {
+        if (a->accumulate) {
+            SPX_CUDA(cudaMemcpyAsync(d_welch, a->welch_acc, (size_t)S * N * sizeof(double), cudaMemcpyHostToDevice, pl->s_compute));
+            h2d += S * N * (long long)sizeof(double);
+        } else {
+            SPX_CUDA(cudaMemsetAsync(d_welch, 0, (size_t)S * N * sizeof(double), pl->s_compute));
+        }
+    }
+    if (d_max) {
+        if (a->accumulate) {
+            SPX_CUDA(cudaMemcpyAsync(d_max, a->maxhold, (size_t)S * N * sizeof(float), cudaMemcpyHostToDevice, pl->s_compute));
+            h2d += S * N * (long long)sizeof(float);
+        } else {
+            SPX_CUDA(cudaMemsetAsync(d_max, 0, (size_t)S * N * sizeof(float), pl->s_compute));
+        }
+    }
+
+    // piece size: big enough to amortise launches, small enough to overlap (about 8-16 MiB)
+    long long piece = (long long)(pl->piece_bytes / elt);
+    if (piece < (long long)N * 4) piece = (long long)N * 4;
+    struct Piece { long long s, f_lo, f_hi; };
+    std::vector<Piece> pieces;
+    size_t ev = 0;
+    for (long long s = 0; s < S; ++s) {
+        const char* h_in = (const char*)a->in + (size_t)(s * stride_host) * elt;
+        char* dd = d_in + (size_t)(s * L) * elt;
+        long long f_lo = 0;
+        for (long long lo = 0; lo < L; lo += piece) {
+            const long long hi = lo + piece < L ? lo + piece : L;
+            SPX_CUDA(cudaMemcpyAsync(dd + (size_t)lo * elt, h_in + (size_t)lo * elt, (size_t)(hi - lo) * elt,
+                                     cudaMemcpyHostToDevice, pl->s_h2d));
+            h2d += (hi - lo) * (long long)elt;
+            long long f_hi = spx_frame_count(hi, N, hop);
+            if (hi == L) f_hi = F;
+            if (f_hi <= f_lo) continue;
+            cudaEvent_t e_in, e_k;
+            SPX_TRY(plan_event(pl, ev++, &e_in));
+            SPX_TRY(plan_event(pl, ev++, &e_k));
+            SPX_CUDA(cudaEventRecord(e_in, pl->s_h2d));
+            SPX_CUDA(cudaStreamWaitEvent(pl->s_compute, e_in, 0));
+            const size_t r0 = (size_t)(s * F + f_lo);
+            SPX_TRY(stft_launch_device(pl, dd + (size_t)(f_lo * hop) * elt, 1, 0, f_hi - f_lo,
+                                       d_db ? d_db + r0 * N : nullptr, d_wf ? d_wf + r0 * N : nullptr,
+                                       d_spec ? d_spec + r0 * N : nullptr, d_welch ? d_welch + s * N : nullptr,
+                                       d_max ? d_max + s * N : nullptr, a->vmin, a->vmax, pl->s_compute));
+            SPX_CUDA(cudaEventRecord(e_k, pl->s_compute));
+            pieces.push_back({s, f_lo, f_hi});
+            f_lo = f_hi;
+        }
+    }
+    // drain rows as their kernels finish
+    size_t evi = 1;
+    for (const Piece& pc : pieces) {
+        cudaEvent_t e_k = pl->events[evi];
+        evi += 2;
+        if (!(d_db || d_wf || d_spec)) continue;
+        SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, e_k, 0));
+        const size_t r0 = (size_t)(pc.s * F + pc.f_lo), nr = (size_t)(pc.f_hi - pc.f_lo);
+        if (d_db) {
+            SPX_CUDA(cudaMemcpyAsync(a->db_rows + r0 * N, d_db + r0 * N, nr * N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_d2h));
+            d2h += (long long)(nr * N * sizeof(float));
+        }
+        if (d_wf) {
+            SPX_CUDA(cudaMemcpyAsync(a->wf_rows + r0 * N, d_wf + r0 * N, nr * N, cudaMemcpyDeviceToHost, pl->s_d2h));
+            d2h += (long long)(nr * N);
+        }
+        if (d_spec) {
+            SPX_CUDA(cudaMemcpyAsync(a->spec_rows + r0 * N * 2, d_spec + r0 * N, nr * N * sizeof(float2), cudaMemcpyDeviceToHost, pl->s_d2h));
+            d2h += (long long)(nr * N * sizeof(float2));
+        }
+    }
+    if (d_welch) {
+        SPX_CUDA(cudaMemcpyAsync(a->welch_acc, d_welch, (size_t)S * N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_compute));
+        d2h += S * N * (long long)sizeof(double);
+    }
+    if (d_max) {
+        SPX_CUDA(cudaMemcpyAsync(a->maxhold, d_max, (size_t)S * N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_compute));
+        d2h += S * N * (long long)sizeof(float);
+    }
+    SPX_CUDA(cudaStreamSynchronize(pl->s_h2d));
+    SPX_CUDA(cudaStreamSynchronize(pl->s_compute));
+    SPX_CUDA(cudaStreamSynchronize(pl->s_d2h));
+    a->h2d_bytes_out = h2d;
+    a->d2h_bytes_out = d2h;
+    return SPX_OK;
+}
+
+__global__ void welch_finalize_kernel(const double* __restrict__ acc, int n, double inv_norm, double* pxx, double* pxx_db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = acc[i] * inv_norm;
+    if (pxx) pxx[i] = v;
+    if (pxx_db) pxx_db[i] = 10.0 * log10(v);
+}
+
+}  // namespace spx
+
+using namespace spx;
+
+// =================================================================== extern "C"
+extern "C" {
+
+int spx_abi_version(void) { return SPX_ABI_VERSION; }
+const char* spx_last_error(void) { return g_err; }
+
+int spx_device_count(int* count) {
+    if (!count) return spx_set_error(SPX_E_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return spx_set_error(SPX_E_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return SPX_OK;
+}
+
+int spx_get_device_info(int device, spx_device_info* out) {
+    if (!out) return spx_set_error(SPX_E_INVALID, "out is NULL");
+    cudaDeviceProp pr;
+    SPX_CUDA(cudaGetDeviceProperties(&pr, device));
+    memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(*out);
+    out->sm_count = pr.multiProcessorCount;
+    out->cc_major = pr.major;
+    out->cc_minor = pr.minor;
+    out->l2_bytes = pr.l2CacheSize;
+    out->max_smem_optin = (int)pr.sharedMemPerBlockOptin;
+    out->total_mem = (int64_t)pr.totalGlobalMem;
+    strncpy(out->name, pr.name, sizeof(out->name) - 1);
+    return SPX_OK;
+}
+
+int64_t spx_frame_count(int64_t n_samples, int32_t nfft, int32_t hop) {
+    if (nfft <= 0 || hop <= 0 || n_samples < nfft) return 0;
+    return (n_samples - nfft) / hop + 1;
+}
+
+int spx_host_alloc(void** out, size_t bytes) {
+    if (!out) return spx_set_error(SPX_E_INVALID, "out is NULL");
+    SPX_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return SPX_OK;
+}
+int spx_host_free(void* p) {
+    if (p) SPX_CUDA(cudaFreeHost(p));
+    return SPX_OK;
+}
+int spx_host_register(void* p, size_t bytes) {
+    SPX_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return SPX_OK;
+}
+int spx_host_unregister(void* p) {
+    SPX_CUDA(cudaHostUnregister(p));
+    return SPX_OK;
+}
+
+int spx_device_alloc(int device, void** out, size_t bytes) {
+    if (!out) return spx_set_error(SPX_E_INVALID, "out is NULL");
+    SPX_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return spx_set_error(SPX_E_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return SPX_OK;
+}
+int spx_device_free(int device, void* p) {
+    SPX_CUDA(cudaSetDevice(device));
+    if (p) SPX_CUDA(cudaFree(p));
+    return SPX_OK;
+}
+int spx_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) {
+    SPX_CUDA(cudaSetDevice(device));
+    SPX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return SPX_OK;
+}
+int spx_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
+    SPX_CUDA(cudaSetDevice(device));
+    SPX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SPX_OK;
+}
+int spx_memset(int device, void* dst, int value, size_t bytes) {
+    SPX_CUDA(cudaSetDevice(device));
+    SPX_CUDA(cudaMemset(dst, value, bytes));
+    return SPX_OK;
+}
+int spx_device_sync(int device) {
+    SPX_CUDA(cudaSetDevice(device));
+    SPX_CUDA(cudaDeviceSynchronize());
+    return SPX_OK;
+}
+
+int spx_plan_create(spx_plan** out, const spx_plan_config* cfg) {
+    if (!out || !cfg) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(spx_plan_config))
+        return spx_set_error(SPX_E_INVALID, "spx_plan_config.struct_size %u != %zu", cfg->struct_size, sizeof(spx_plan_config));
+    if (!is_pow2(cfg->nfft) || cfg->nfft < 16 || cfg->nfft > (1 << 20))
+        return spx_set_error(SPX_E_UNSUPPORTED, "nfft %d must be a power of two in [16, 1048576]", cfg->nfft);
+    if (cfg->hop < 1 || cfg->hop > cfg->nfft) return spx_set_error(SPX_E_INVALID, "hop %d must be in [1, nfft]", cfg->hop);
+    if (cfg->window < 0 || cfg->window > 2) return spx_set_error(SPX_E_INVALID, "unknown window %d", cfg->window);
+    if (cfg->in_fmt != SPX_FMT_CF32 && cfg->in_fmt != SPX_FMT_CI16) return spx_set_error(SPX_E_INVALID, "unknown in_fmt %d", cfg->in_fmt);
+    int ndev = 0;
+    SPX_TRY(spx_device_count(&ndev));
+    if (ndev == 0) return spx_set_error(SPX_E_NODEVICE, "no CUDA device (libspx has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return spx_set_error(SPX_E_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    SPX_CUDA(cudaSetDevice(cfg->device));
+
+    spx_plan* pl = new (std::nothrow) spx_plan();
+    if (!pl) return spx_set_error(SPX_E_NOMEM, "out of host memory");
+    pl->cfg = *cfg;
+    if (!(pl->cfg.in_scale != 0.0f)) pl->cfg.in_scale = 1.0f;
+    int rc = SPX_OK;
+    do {
+        cudaError_t e;
+        if ((e = cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, cfg->device)) != cudaSuccess) { rc = spx_set_error(SPX_E_CUDA, "%s", cudaGetErrorString(e)); break; }
+        // window (float64 as numpy builds it, scaled, rounded once to float)
+        pl->win64 = build_window_f64(cfg->window, cfg->nfft);
+        pl->sum_w2 = 0.0;
+        pl->sum_w = 0.0;
+        for (double w : pl->win64) { pl->sum_w2 += w * w; pl->sum_w += w; }
+        if (cfg->window != SPX_WINDOW_RECT || pl->cfg.in_scale != 1.0f) {
+            std::vector<float> wf((size_t)cfg->nfft);
+            for (int i = 0; i < cfg->nfft; ++i) wf[i] = (float)(pl->win64[i] * (double)pl->cfg.in_scale);
+            if ((e = cudaMalloc(&pl->d_win, wf.size() * sizeof(float))) != cudaSuccess) { rc = spx_set_error(SPX_E_NOMEM, "%s", cudaGetErrorString(e)); break; }
+            if ((e = cudaMemcpy(pl->d_win, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = spx_set_error(SPX_E_CUDA, "%s", cudaGetErrorString(e)); break; }
+        }
+        if (cfg->nfft <= 8192) {
+            std::vector<float2> tw = build_twiddles(cfg->nfft);
+            if ((e = cudaMalloc(&pl->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { rc = spx_set_error(SPX_E_NOMEM, "%s", cudaGetErrorString(e)); break; }
+            if ((e = cudaMemcpy(pl->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = spx_set_error(SPX_E_CUDA, "%s", cudaGetErrorString(e)); break; }
+        }
+        if ((e = cudaStreamCreateWithFlags(&pl->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&pl->s_h2d, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&pl->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) { rc = spx_set_error(SPX_E_CUDA, "%s", cudaGetErrorString(e)); break; }
+    } while (0);
+    if (rc != SPX_OK) {
+        spx_plan_destroy(pl);
+        return rc;
+    }
+    *out = pl;
+    return SPX_OK;
+}
+
+int spx_plan_destroy(spx_plan* pl) {
+    if (!pl) return SPX_OK;
+    cudaSetDevice(pl->cfg.device);
+    if (pl->s_compute) { cudaStreamSynchronize(pl->s_compute); cudaStreamDestroy(pl->s_compute); }
+    if (pl->s_h2d) { cudaStreamSynchronize(pl->s_h2d); cudaStreamDestroy(pl->s_h2d); }
+    if (pl->s_d2h) { cudaStreamSynchronize(pl->s_d2h); cudaStreamDestroy(pl->s_d2h); }
+    for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
+    if (pl->d_win) cudaFree(pl->d_win);
+    if (pl->d_tw) cudaFree(pl->d_tw);
+    pl->st_in.release(); pl->st_db.release(); pl->st_wf.release(); pl->st_spec.release();
+    pl->st_welch.release(); pl->st_max.release(); pl->st_misc.release(); pl->st_flush.release();
+    delete pl;
+    return SPX_OK;
+}
+
+int spx_plan_sync(spx_plan* pl) {
+    if (!pl) return spx_set_error(SPX_E_INVALID, "plan is NULL");
+    std::lock_guard<std::mutex> g(pl->mu);
+    SPX_CUDA(cudaSetDevice(pl->cfg.device));
+    SPX_CUDA(cudaStreamSynchronize(pl->s_h2d));
+    SPX_CUDA(cudaStreamSynchronize(pl->s_compute));
+    SPX_CUDA(cudaStreamSynchronize(pl->s_d2h));
+    return SPX_OK;
+}
+
+int spx_plan_window_sums(spx_plan* pl, double* sum_w2, double* sum_w) {
+    if (!pl) return spx_set_error(SPX_E_INVALID, "plan is NULL");
+    if (sum_w2) *sum_w2 = pl->sum_w2;  // window only: in_scale belongs to the data
+    if (sum_w) *sum_w = pl->sum_w;
+    return SPX_OK;
+}
+
+int spx_stft_exec(spx_plan* pl, spx_stft_args* a) {
+    if (!pl || !a) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    if (a->struct_size != sizeof(spx_stft_args))
+        return spx_set_error(SPX_E_INVALID, "spx_stft_args.struct_size %u != %zu", a->struct_size, sizeof(spx_stft_args));
+    if (a->n_streams < 1) return spx_set_error(SPX_E_INVALID, "n_streams must be >= 1");
+    if (a->n_samples < 0) return spx_set_error(SPX_E_INVALID, "n_samples < 0");
+    if (a->mem != SPX_MEM_HOST && a->mem != SPX_MEM_DEVICE) return spx_set_error(SPX_E_INVALID, "unknown mem %d", a->mem);
+    if ((a->wf_rows != nullptr) && !(a->vmax > a->vmin)) return spx_set_error(SPX_E_INVALID, "wf_rows needs vmax > vmin");
+    if (a->n_streams > 1 && a->stream_stride < a->n_samples && a->mem == SPX_MEM_HOST)
+        return spx_set_error(SPX_E_INVALID, "stream_stride < n_samples");
+    const long long F = spx_frame_count(a->n_samples, pl->cfg.nfft, pl->cfg.hop);
+    a->n_frames_out = F;
+    a->h2d_bytes_out = 0;
+    a->d2h_bytes_out = 0;
+    std::lock_guard<std::mutex> g(pl->mu);
+    SPX_CUDA(cudaSetDevice(pl->cfg.device));
+    const int N = pl->cfg.nfft;
+    const long long S = a->n_streams;
+    if (a->in == nullptr && F > 0) return spx_set_error(SPX_E_INVALID, "in is NULL");
+    if (a->mem == SPX_MEM_DEVICE) {
+        cudaStream_t st = a->stream ? (cudaStream_t)a->stream : pl->s_compute;
+        if (!a->accumulate) {
+            if (a->welch_acc) SPX_CUDA(cudaMemsetAsync(a->welch_acc, 0, (size_t)S * N * sizeof(double), st));
+            if (a->maxhold) SPX_CUDA(cudaMemsetAsync(a->maxhold, 0, (size_t)S * N * sizeof(float), st));
+        }
+        return stft_launch_device(pl, a->in, S, a->stream_stride, F, a->db_rows, a->wf_rows,
+                                  reinterpret_cast<float2*>(a->spec_rows), a->welch_acc, a->maxhold, a->vmin, a->vmax, st);
+    }
+    if (F == 0) {
+        if (!a->accumulate) {
+            if (a->welch_acc) memset(a->welch_acc, 0, (size_t)S * N * sizeof(double));
+            if (a->maxhold) memset(a->maxhold, 0, (size_t)S * N * sizeof(float));
+        }
+        return SPX_OK;
+    }
+    return stft_exec_host(pl, a, F);
+}
+
+int spx_stft_time(spx_plan* pl, spx_stft_args* a, int32_t warmup, int32_t iters, int32_t flush_l2, float* ms_each) {
+    if (!pl || !a || !ms_each || iters < 1 || warmup < 0) return spx_set_error(SPX_E_INVALID, "bad argument");
+    if (a->mem != SPX_MEM_DEVICE) return spx_set_error(SPX_E_INVALID, "spx_stft_time needs SPX_MEM_DEVICE buffers");
+    cudaEvent_t e0, e1;
+    size_t flush_bytes = 256u << 20;
+    {
+        std::lock_guard<std::mutex> g(pl->mu);
+        SPX_CUDA(cudaSetDevice(pl->cfg.device));
+        if (flush_l2) SPX_TRY(pl->st_flush.reserve(flush_bytes));
+    }
+    SPX_CUDA(cudaEventCreate(&e0));
+    SPX_CUDA(cudaEventCreate(&e1));
+    cudaStream_t st = a->stream ? (cudaStream_t)a->stream : pl->s_compute;
+    int rc = SPX_OK;
+    for (int i = 0; i < warmup + iters && rc == SPX_OK; ++i) {
+        if (flush_l2) cudaMemsetAsync(pl->st_flush.ptr, i & 0xff, flush_bytes, st);
+        cudaEventRecord(e0, st);
+        rc = spx_stft_exec(pl, a);
+        cudaEventRecord(e1, st);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (rc == SPX_OK && e != cudaSuccess) rc = spx_set_error(SPX_E_CUDA, "kernel failed: %s", cudaGetErrorString(e));
+        if (rc == SPX_OK && i >= warmup) cudaEventElapsedTime(&ms_each[i - warmup], e0, e1);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+int spx_welch_finalize(spx_plan* pl, int32_t mem, const double* welch_acc, int64_t n_frames, double fs, double* pxx,
+                       double* pxx_db, void* stream) {
+    if (!pl || !welch_acc) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    if (n_frames < 1 || !(fs > 0)) return spx_set_error(SPX_E_INVALID, "n_frames and fs must be positive");
+    std::lock_guard<std::mutex> g(pl->mu);
+    SPX_CUDA(cudaSetDevice(pl->cfg.device));
+    const int N = pl->cfg.nfft;
+    // mlab.psd: |X|^2 / (Fs * sum(w^2)), mean over frames.  in_scale is part of the data, not of the window.
+    const double inv = 1.0 / ((double)n_frames * fs * pl->sum_w2);
+    if (mem == SPX_MEM_DEVICE) {
+        cudaStream_t st = stream ? (cudaStream_t)stream : pl->s_compute;
+        welch_finalize_kernel<<<(N + 255) / 256, 256, 0, st>>>(welch_acc, N, inv, pxx, pxx_db);
+        SPX_CUDA(cudaGetLastError());
+        return SPX_OK;
+    }
+    SPX_TRY(pl->st_misc.reserve((size_t)N * sizeof(double) * 3));
+    double* d = (double*)pl->st_misc.ptr;
+    SPX_CUDA(cudaMemcpyAsync(d, welch_acc, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, pl->s_compute));
+    welch_finalize_kernel<<<(N + 255) / 256, 256, 0, pl->s_compute>>>(d, N, inv, pxx ? d + N : nullptr, pxx_db ? d + 2 * N : nullptr);
+    SPX_CUDA(cudaGetLastError());
+    if (pxx) SPX_CUDA(cudaMemcpyAsync(pxx, d + N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_compute));
+    if (pxx_db) SPX_CUDA(cudaMemcpyAsync(pxx_db, d + 2 * N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_compute));
+    SPX_CUDA(cudaStreamSynchronize(pl->s_compute));
+    return SPX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// spx_plan.h -- the opaque plan object behind include/spx.h (host-side only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <vector>
+
+#include "spx_internal.h"
+
+namespace spx {
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);  // grow-only
+    void release();
+};
+
+}  // namespace spx
+
+struct spx_plan {
+    spx_plan_config cfg{};
+    int sm_count = 0;
+    float* d_win = nullptr;   // window * in_scale (nullptr: rect and scale 1)
+    float2* d_tw = nullptr;   // twiddle table of the shared-memory kernel (nfft <= 8192)
+    std::vector<double> win64;
+    double sum_w2 = 0.0, sum_w = 0.0;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> events;
+    size_t piece_bytes = 16u << 20;  // H2D piece size of the host pipeline
+    // staging for SPX_MEM_HOST execution (grow-only)
+    spx::DevBuf st_in, st_db, st_wf, st_spec, st_welch, st_max, st_misc, st_flush;
+    std::mutex mu;
+};
+
+namespace spx {
+int plan_event(spx_plan* pl, size_t i, cudaEvent_t* out);
+int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long long stream_stride, long long frames,
+                       float* db_rows, unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold,
+                       float vmin, float vmax, cudaStream_t st);
+}  // namespace spx

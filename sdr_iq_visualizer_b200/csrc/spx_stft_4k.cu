@@ -1,0 +1,15 @@
+// N = 4096 instantiations of the fused STFT kernel (K1), including tuning variants.
+#include "spx_stft_kernel.cuh"
+
+namespace spx {
+int launch_stft_4k(StftLaunch& L) {
+    switch (L.variant) {
+        case 0: return launch_stft_n<4096, TW_LDG, 2>(L);
+        case 1: return launch_stft_n<4096, TW_LDG, 3>(L);
+        case 2: return launch_stft_n<4096, TW_REG, 2>(L);
+        case 3: return launch_stft_n<4096, TW_REG, 3>(L);
+        case 4: return launch_stft_n<4096, TW_SMEM, 2>(L);
+        default: return spx_set_error(SPX_E_INVALID, "unknown kernel variant %d for nfft 4096", L.variant);
+    }
+}
+}  // namespace spx

@@ -1,0 +1,286 @@
+// spx_stft_device.cuh -- per-thread phases of the fused STFT kernel (K1).
+//
+// One frame = unpack (int16|cf32) -> window -> Stockham FFT -> |X|^2 -> dB -> fftshift ->
+// {f32 dB row, u8 waterfall row, Welch sum, max-hold}.  Replaces, fused and batched, the three
+// lines /root/reference/app/sdr/streamer.py:119-121 and the mlab.psd frame loop behind
+// /root/reference/scripts/process_sigmf_data.py:188.
+//
+// Everything here is __host__ __device__: the CUDA kernel (spx_stft.cu) and the CPU
+// re-execution used by the `-m "not gpu"` tests (csrc/emul) share this code verbatim.
+#pragma once
+#include "spx_fft_core.cuh"
+
+namespace spx {
+
+enum { FMT_CF32 = 0, FMT_CI16 = 1 };
+enum { TW_LDG = 0, TW_REG = 1, TW_SMEM = 2 };
+
+struct StftParams {
+    const void* in;              // cf32 (float2) or ci16 (short2) samples
+    long long stream_stride;     // samples between consecutive streams
+    long long frames_per_stream; // F
+    int n_streams;
+    int hop;
+    const float* win;            // [N] window * in_scale, or nullptr (rect, scale 1)
+    const float2* tw;            // twiddle table, plan_tw_size(N) entries
+    float* db_rows;              // [n_streams*F][N] dB rows (fftshift order) or nullptr
+    unsigned char* wf_rows;      // [n_streams*F][N] u8 colormap indices or nullptr
+    float2* spec_rows;           // [n_streams*F][N] complex spectrum (fftshift order) or nullptr
+    double* welch_acc;           // [n_streams][N]  += sum_f |X|^2   (fftshift order) or nullptr
+    float* maxhold;              // [n_streams][N]  max= |X|^2       (fftshift order) or nullptr
+    float db_eps;                // 20*log10(|X| + db_eps)
+    float q_vmin, q_scale;       // u8 = sat(floor((db - vmin) * scale)), scale = 256/(vmax-vmin)
+    int frames_per_chunk;        // accumulator flush granularity (<= 256)
+    int chunks_per_stream;
+    long long total_chunks;
+};
+
+// ------------------------------------------------------------------ device/host primitives
+SPX_HD float2 ld_stream_cf32(const float2* p) {
+#ifdef __CUDA_ARCH__
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+SPX_HD float2 ld_stream_ci16(const short2* p) {
+#ifdef __CUDA_ARCH__
+    unsigned int w;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(w) : "l"(p));
+    short lo = (short)(w & 0xffffu), hi = (short)(w >> 16);
+    return make_float2((float)lo, (float)hi);
+#else
+    return make_float2((float)p->x, (float)p->y);
+#endif
+}
+template <typename T>
+SPX_HD T ld_keep(const T* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+SPX_HD float fast_sqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+SPX_HD float fast_log2(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return log2f(x);
+#endif
+}
+// saturating floor-convert to u8: NaN -> 0, -inf -> 0, +inf -> 255
+SPX_HD unsigned int sat_floor_u8(float q) {
+#ifdef __CUDA_ARCH__
+    unsigned int r;
+    asm("cvt.rmi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(q));
+    return r;
+#else
+    if (!(q == q)) return 0u;
+    float f = floorf(q);
+    return f < 0.f ? 0u : (f > 255.f ? 255u : (unsigned int)f);
+#endif
+}
+#define SPX_DB_PER_LOG2 6.02059991327962390427f  // 20*log10(2)
+
+SPX_HD float amp_db(float pw, float eps) { return SPX_DB_PER_LOG2 * fast_log2(fast_sqrt(pw) + eps); }
+
+// ------------------------------------------------------------------ per-thread state
+template <bool ACC>
+struct StftAcc {
+    float sum[ACC ? 16 : 1];
+    float mx[ACC ? 16 : 1];
+    SPX_HD void reset() {
+#pragma unroll
+        for (int i = 0; i < (ACC ? 16 : 1); ++i) { sum[i] = 0.f; mx[i] = 0.f; }
+    }
+};
+
+// twiddle bases kept in registers (TW_REG): per pass s >= 1 the entries t in {1,2,3,4,8,12}
+template <int N>
+struct TwRegs {
+    float2 b[(plan_passes(N) > 1 ? plan_passes(N) - 1 : 1) * 6];
+};
+
+template <int R> SPX_HD constexpr int tw_base_slot(int t) {
+    // slot of base t in {1,2,3,4,8,12}
+    return t == 1 ? 0 : t == 2 ? 1 : t == 3 ? 2 : t == 4 ? 3 : t == 8 ? 4 : 5;
+}
+
+template <int N, int S>
+SPX_HD void tw_regs_load_pass(TwRegs<N>& r, int tid, const float2* tw) {
+    constexpr int R = plan_radix(N, S), NS = plan_ns(N, S), OFF = plan_tw_offset(N, S);
+    // only valid when the thread has one butterfly in this pass (R == 16) or all its butterflies
+    // share jm (never) -- so TW_REG is restricted to plans whose passes >= 1 are all radix 16.
+    static_assert(R == 16, "TW_REG needs radix-16 passes");
+    const int jm = tid & (NS - 1);
+    constexpr int ts[6] = {1, 2, 3, 4, 8, 12};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) r.b[(S - 1) * 6 + q] = ld_keep(tw + OFF + (ts[q] - 1) * NS + jm);
+}
+
+// ------------------------------------------------------------------ pass pieces
+template <int N, int FMT>
+SPX_HD void load_frame(float2* v, const StftParams& p, long long sample0, int tid) {
+    constexpr int T = N / 16;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const long long i = sample0 + tid + t * T;
+        if (FMT == FMT_CF32) v[t] = ld_stream_cf32(reinterpret_cast<const float2*>(p.in) + i);
+        else                 v[t] = ld_stream_ci16(reinterpret_cast<const short2*>(p.in) + i);
+    }
+    if (p.win != nullptr) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const float w = ld_keep(p.win + tid + t * T);
+            v[t].x *= w;
+            v[t].y *= w;
+        }
+    }
+}
+
+template <int N, int S>
+SPX_HD void pass_load_smem(float2* v, int tid, const float2* src) {
+    constexpr int R = plan_radix(N, S), NB = 16 / R, T = N / 16;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        const int j = tid + T * u;
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const int i = j + t * (N / R);
+            v[u * R + t] = src[S == 1 ? pad0(i) : i];
+        }
+    }
+}
+
+template <int N, int S, bool TW_IN_SMEM>
+SPX_HD void pass_twiddle_table(float2* v, int tid, const float2* tw) {
+    constexpr int R = plan_radix(N, S), NB = 16 / R, T = N / 16;
+    constexpr int NS = plan_ns(N, S), OFF = plan_tw_offset(N, S);
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        const int jm = (tid + T * u) & (NS - 1);
+#pragma unroll
+        for (int t = 1; t < R; ++t) {
+            const float2* wp = tw + OFF + (t - 1) * NS + jm;
+            v[u * R + t] = cmul(v[u * R + t], TW_IN_SMEM ? *wp : ld_keep(wp));
+        }
+    }
+}
+
+template <int N, int S>
+SPX_HD void pass_twiddle_regs(float2* v, const TwRegs<N>& r) {
+    // radix 16 only: W^{t jm}, t = 4a + b  ->  base[4a] * base[b]
+    const float2* b = r.b + (S - 1) * 6;
+    const float2 w1 = b[0], w2 = b[1], w3 = b[2], w4 = b[3], w8 = b[4], w12 = b[5];
+    v[1] = cmul(v[1], w1);  v[2] = cmul(v[2], w2);  v[3] = cmul(v[3], w3);
+    v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], cmul(w4, w1));  v[6] = cmul(v[6], cmul(w4, w2));  v[7] = cmul(v[7], cmul(w4, w3));
+    v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1));  v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+    v[12] = cmul(v[12], w12);
+    v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
+}
+
+template <int N, int S>
+SPX_HD void pass_dft(float2* v) {
+    constexpr int R = plan_radix(N, S), NB = 16 / R;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) dft<R>(v + u * R);
+}
+
+template <int N, int S>
+SPX_HD void pass_store_smem(const float2* v, int tid, float2* dst) {
+    constexpr int R = plan_radix(N, S), NB = 16 / R, T = N / 16, NS = plan_ns(N, S);
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        const int j = tid + T * u;
+        const int jm = j & (NS - 1);
+        const int base = (j - jm) * R + jm;
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const int i = base + t * NS;
+            dst[S == 0 ? pad0(i) : i] = v[u * R + t];
+        }
+    }
+}
+
+// bin held in v[u*R + t] after the last pass
+template <int N>
+SPX_HD int out_bin(int tid, int u, int t) {
+    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S), T = N / 16;
+    return tid + T * u + t * (N / R);
+}
+
+// ------------------------------------------------------------------ fused epilogue
+template <int N, bool ACC>
+SPX_HD void epilogue(const float2* v, int tid, const StftParams& p, long long row, StftAcc<ACC>& acc) {
+    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S), NB = 16 / R;
+    float* db_row = p.db_rows ? p.db_rows + row * N : nullptr;
+    unsigned char* wf_row = p.wf_rows ? p.wf_rows + row * N : nullptr;
+    float2* sp_row = p.spec_rows ? p.spec_rows + row * N : nullptr;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const float2 x = v[u * R + t];
+            const int pos = (out_bin<N>(tid, u, t) + N / 2) & (N - 1);  // fftshift (streamer.py:119)
+            const float pw = x.x * x.x + x.y * x.y;
+            if (ACC) {
+                acc.sum[u * R + t] += pw;
+                acc.mx[u * R + t] = fmaxf(acc.mx[u * R + t], pw);
+            }
+            if (sp_row) sp_row[pos] = x;
+            if (db_row || wf_row) {
+                const float db = amp_db(pw, p.db_eps);  // 20*log10(|X| + eps)  (streamer.py:121)
+                if (db_row) db_row[pos] = db;
+                if (wf_row) wf_row[pos] = (unsigned char)sat_floor_u8((db - p.q_vmin) * p.q_scale);
+            }
+        }
+    }
+}
+
+// what a flush writes: (slot position, value) pairs are produced by the caller with atomics
+template <int N>
+SPX_HD int acc_pos(int tid, int idx) {
+    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S);
+    return (out_bin<N>(tid, idx / R, idx % R) + N / 2) & (N - 1);
+}
+
+// ------------------------------------------------------------------ one frame, phase by phase
+// phase k (0 <= k < P) = pass k; barriers between phases are the caller's job.
+template <int N, int FMT, bool ACC, int TWM, int S>
+SPX_HD void stft_phase(float2* v, int tid, const StftParams& p, long long sample0, long long row, bool active,
+                       float2* bufA, float2* bufB, const float2* tw, const TwRegs<N>& twr, StftAcc<ACC>& acc) {
+    constexpr int P = plan_passes(N);
+    if (!active) return;
+    if constexpr (S == 0) {
+        load_frame<N, FMT>(v, p, sample0, tid);
+    } else {
+        const float2* src = ((S - 1) & 1) ? bufB : bufA;
+        pass_load_smem<N, S>(v, tid, src);
+        if constexpr (TWM == TW_REG) pass_twiddle_regs<N, S>(v, twr);
+        else pass_twiddle_table<N, S, TWM == TW_SMEM>(v, tid, tw);
+    }
+    pass_dft<N, S>(v);
+    if constexpr (S == P - 1) {
+        epilogue<N, ACC>(v, tid, p, row, acc);
+    } else {
+        float2* dst = (S & 1) ? bufB : bufA;
+        pass_store_smem<N, S>(v, tid, dst);
+    }
+}
+
+}  // namespace spx

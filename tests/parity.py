@@ -1,0 +1,59 @@
+"""Parity rules shared by the emulator (CPU) and GPU tests (BASELINE.json north_star).
+
+On identical inputs, against the float64 oracle:
+  * integer / indexing outputs are bit-exact (frame slicing, fftshift order, histogram counts);
+    uint8 colormap indices are bit-exact except where the oracle's pre-floor value is within 1e-3
+    of an integer (threshold ties);
+  * dB rows / PSD: |delta| <= 1e-3 dB on bins at or above the row's noise floor (20th percentile of
+    the oracle row); on the bins below it the linear power must agree to <= 1e-4 of the noise-floor
+    power (a dB difference is meaningless for a bin that is a random deep null).
+"""
+import numpy as np
+
+DB_TOL = 1e-3
+REL_TOL = 1e-4
+TIE_TOL = 1e-3
+
+
+def check_db_rows(db_got, power_ref, eps=1e-12, what=""):
+    """db_got: [F,N] float; power_ref: [F,N] float64 |X|^2 (same order)."""
+    db_got = np.asarray(db_got, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        db_ref = 20 * np.log10(np.sqrt(power_ref) + eps)
+    floor_db = np.percentile(db_ref, 20, axis=-1, keepdims=True)
+    above = db_ref >= floor_db
+    err_db = np.abs(db_got - db_ref)
+    worst_above = float(err_db[above].max()) if above.any() else 0.0
+    assert worst_above <= DB_TOL, f"{what}: {worst_above:.3e} dB error above the noise floor"
+    floor_pw = (10 ** (floor_db / 20) - eps).clip(min=0) ** 2
+    pw_got = (10 ** (db_got / 20) - eps).clip(min=0) ** 2
+    rel = np.abs(pw_got - power_ref) / np.maximum(floor_pw, 1e-300)
+    below = ~above
+    worst_below = float(rel[below].max()) if below.any() else 0.0
+    assert worst_below <= REL_TOL, f"{what}: linear error {worst_below:.3e} of the floor power below the floor"
+    return worst_above, worst_below
+
+
+def check_power(p_got, p_ref, what="", rel_tol=REL_TOL):
+    """Welch sums / max-hold / PSD: per-bin relative error in linear power, and the dB bound."""
+    p_got = np.asarray(p_got, dtype=np.float64)
+    p_ref = np.asarray(p_ref, dtype=np.float64)
+    rel = np.abs(p_got - p_ref) / np.maximum(np.abs(p_ref), 1e-300)
+    worst = float(rel.max()) if rel.size else 0.0
+    assert worst <= rel_tol, f"{what}: relative error {worst:.3e}"
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ddb = np.abs(10 * np.log10(p_got) - 10 * np.log10(p_ref))
+    ddb = ddb[np.isfinite(ddb)]
+    if ddb.size:
+        assert ddb.max() <= DB_TOL, f"{what}: {ddb.max():.3e} dB"
+    return worst
+
+
+def check_u8(q_got, db_ref, vmin, vmax, what=""):
+    """bit-exact away from threshold ties (oracle pre-floor value within 1e-3 of an integer)."""
+    pre = (np.asarray(db_ref, dtype=np.float64) - vmin) * (256.0 / (vmax - vmin))
+    want = np.clip(np.nan_to_num(np.floor(pre), nan=0.0, posinf=255.0, neginf=0.0), 0, 255).astype(np.uint8)
+    tie = np.abs(pre - np.rint(pre)) <= TIE_TOL
+    bad = (np.asarray(q_got) != want) & ~tie
+    assert not bad.any(), f"{what}: {int(bad.sum())} colormap indices differ away from ties"
+    return int(((np.asarray(q_got) != want) & tie).sum()), int(tie.sum())

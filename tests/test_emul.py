@@ -1,0 +1,145 @@
+"""CPU re-execution of the CUDA kernel's per-thread code (tests/emul) against the oracle.
+Checks the Stockham index maps, padding, twiddle tables, fused epilogue and chunked accumulation
+for every supported shared-memory FFT size -- without a GPU.  The emulator is test infrastructure;
+the product never links it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import spectral_ref as sref
+from tests import parity
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL_DIR = os.path.join(HERE, "emul")
+EMUL_SO = os.path.join(EMUL_DIR, "libspx_emul.so")
+
+
+@pytest.fixture(scope="session")
+def emul():
+    src = os.path.join(EMUL_DIR, "spx_emul.cu")
+    csrc = os.path.join(os.path.dirname(HERE), "sdr_iq_visualizer_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("spx_fft_core.cuh", "spx_stft_device.cuh", "spx_tables.h")]
+    if not os.path.exists(EMUL_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMUL_SO) for d in deps):
+        nvcc = "nvcc" if subprocess.run(["which", "nvcc"], capture_output=True).returncode == 0 else "/usr/local/cuda/bin/nvcc"
+        subprocess.run([nvcc, "-std=c++17", "-O2", "-shared", "-Xcompiler", "-fPIC", "-gencode",
+                        "arch=compute_100a,code=sm_100a", "-o", EMUL_SO, src], check=True, cwd=EMUL_DIR)
+    lib = C.CDLL(EMUL_SO)
+    lib.spx_emul_stft.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_void_p,
+                                                  C.c_float, C.c_float, C.c_float, C.c_int] + [C.c_void_p] * 5
+    lib.spx_emul_plan.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run_emul(lib, x, nfft, hop, kind, fmt=0, scale=1.0, tw_mode=0, n_streams=1, fpc=3, vmin=-60.0, vmax=60.0,
+             eps=1e-12):
+    L = (x.size // 2 if fmt == 1 else x.size) // n_streams
+    F = sref.frame_count(L, nfft, hop)
+    w = None
+    if sref.window_id(kind) != 0 or scale != 1.0:
+        w = (sref.window(kind, nfft) * scale).astype(np.float32)
+    out = dict(db=np.zeros((n_streams * F, nfft), np.float32), wf=np.zeros((n_streams * F, nfft), np.uint8),
+               spec=np.zeros((n_streams * F, nfft, 2), np.float32), welch=np.zeros((n_streams, nfft), np.float64),
+               maxhold=np.zeros((n_streams, nfft), np.float32))
+    rc = lib.spx_emul_stft(nfft, fmt, tw_mode, _p(x), L, n_streams, L, hop, _p(w), eps, vmin, vmax, fpc, _p(out["db"]),
+                           _p(out["wf"]), _p(out["spec"]), _p(out["welch"]), _p(out["maxhold"]))
+    assert rc == 0
+    out["F"] = F
+    out["win32"] = w
+    return out
+
+
+def oracle_power(x, nfft, hop, w32, fmt=0, n_streams=1):
+    """float64 oracle evaluated on exactly what the kernel sees: the float32-rounded window."""
+    xs = sref.as_complex128(x, fmt).reshape(n_streams, -1)
+    w = np.ones(nfft) if w32 is None else w32.astype(np.float64)
+    rows = []
+    for s in range(n_streams):
+        fr = sref.frames(xs[s], nfft, hop)
+        rows.append(sref.shift_bins(np.fft.fft(fr * w, axis=1)))
+    return np.concatenate(rows, axis=0)
+
+
+@pytest.mark.parametrize("nfft", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_plan_factorisation(emul, nfft):
+    rad = (C.c_int * 5)()
+    tws = C.c_int()
+    p = emul.spx_emul_plan(nfft, rad, C.byref(tws))
+    r = list(rad)[:p]
+    assert r[0] == 16 and all(v in (2, 4, 8, 16) for v in r) and int(np.prod(r)) == nfft
+    assert all(v == 0 for v in list(rad)[p:])
+
+
+@pytest.mark.parametrize("nfft,hop,kind", [(16, 16, "rect"), (32, 8, "hann"), (64, 16, "blackman"), (128, 128, "hann"),
+                                           (256, 64, "hann"), (512, 256, "blackman"), (1024, 512, "hann"),
+                                           (2048, 1024, "hann"), (4096, 1024, "hann"), (8192, 4096, "hann")])
+def test_emul_cf32_parity(emul, nfft, hop, kind):
+    L = nfft + hop * 7 + 5  # ragged tail is dropped
+    x = sref.synth_iq(L, seed=nfft + 1).astype(np.complex64)
+    o = run_emul(emul, x, nfft, hop, kind)
+    X = oracle_power(x, nfft, hop, o["win32"])
+    P = X.real**2 + X.imag**2
+    assert o["F"] == 8
+    got = o["spec"][..., 0] + 1j * o["spec"][..., 1]
+    assert np.abs(got - X).max() <= 4e-6 * np.sqrt(P.mean())
+    parity.check_db_rows(o["db"], P, what=f"N={nfft}")
+    parity.check_power(o["welch"][0], P.sum(axis=0), what="welch")
+    parity.check_power(o["maxhold"][0], P.max(axis=0), what="maxhold")
+    parity.check_u8(o["wf"], sref.amplitude_db(X), -60.0, 60.0, what="u8")
+
+
+def test_emul_tone_lands_in_shifted_bin(emul):
+    """fftshift order is an integer permutation: must be exact (streamer.py:119)."""
+    n = 4096
+    for k in (0, 1, 100, 2047, 2048, 4095):
+        x = np.exp(2j * np.pi * k * np.arange(n) / n).astype(np.complex64)
+        o = run_emul(emul, x, n, n, "rect")
+        assert int(np.argmax(o["db"][0])) == (k + n // 2) % n
+
+
+def test_emul_ci16_and_scale(emul):
+    n, hop = 4096, 1024
+    x = sref.to_ci16(sref.synth_iq(n + 9 * hop, seed=2))
+    for scale in (1.0, 2.0**-15):
+        o = run_emul(emul, x, n, hop, "hann", fmt=1, scale=scale, vmin=-40.0, vmax=120.0)
+        X = oracle_power(x, n, hop, o["win32"], fmt=1)
+        P = X.real**2 + X.imag**2
+        parity.check_db_rows(o["db"], P, what=f"ci16 scale={scale}")
+        parity.check_power(o["welch"][0], P.sum(axis=0), what="welch")
+
+
+def test_emul_register_twiddles_match_table(emul):
+    n, hop = 4096, 2048
+    x = sref.synth_iq(n + 3 * hop, seed=4).astype(np.complex64)
+    a = run_emul(emul, x, n, hop, "hann", tw_mode=0)
+    b = run_emul(emul, x, n, hop, "hann", tw_mode=1)
+    X = oracle_power(x, n, hop, a["win32"])
+    P = X.real**2 + X.imag**2
+    parity.check_db_rows(b["db"], P, what="TW_REG")
+    assert np.abs(a["spec"] - b["spec"]).max() <= 2e-6 * np.sqrt(P.mean())
+
+
+def test_emul_multistream_chunking(emul):
+    """chunks never cross a stream; accumulators are per stream (C4 layout)."""
+    n, hop, S = 1024, 512, 3
+    L = n + 10 * hop
+    xs = np.concatenate([sref.synth_iq(L, seed=10 + s, snr_db=5 * (s + 1)) for s in range(S)]).astype(np.complex64)
+    for fpc in (1, 4, 11, 64):
+        o = run_emul(emul, xs, n, hop, "hann", n_streams=S, fpc=fpc)
+        X = oracle_power(xs, n, hop, o["win32"], n_streams=S)
+        P = (X.real**2 + X.imag**2).reshape(S, -1, n)
+        for s in range(S):
+            parity.check_power(o["welch"][s], P[s].sum(axis=0), what=f"welch s={s} fpc={fpc}")
+            parity.check_power(o["maxhold"][s], P[s].max(axis=0), what=f"maxhold s={s}")
+
+
+def test_emul_zero_input_is_minus_240_db(emul):
+    o = run_emul(emul, np.zeros(4096, np.complex64), 4096, 4096, "rect")
+    assert np.abs(o["db"] + 240.0).max() < 1e-3  # 20*log10(0 + 1e-12) (streamer.py:121)
+    assert np.all(o["wf"] == 0)

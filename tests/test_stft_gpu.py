@@ -1,0 +1,229 @@
+"""GPU parity tests of the fused STFT path (K1) through the C ABI, against the float64 oracle and
+the golden vectors generated from the reference.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import spectral_ref as sref
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sp():
+    from sdr_iq_visualizer_b200 import spectral
+    from sdr_iq_visualizer_b200 import _native
+    assert _native.device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    return spectral
+
+
+def oracle_rows(x, nfft, hop, kind, fmt=0, scale=1.0, n_streams=1):
+    xs = sref.as_complex128(x, fmt).reshape(n_streams, -1)
+    w = sref.window(kind, nfft)
+    if sref.window_id(kind) != 0 or scale != 1.0:
+        w = (w * scale).astype(np.float32).astype(np.float64)  # the kernel's float32 table
+    out = []
+    for s in range(n_streams):
+        fr = sref.frames(xs[s], nfft, hop)
+        for i in range(0, fr.shape[0], 1024):
+            out.append(sref.shift_bins(np.fft.fft(fr[i:i + 1024] * w, axis=1)))
+    return np.concatenate(out, axis=0) if out else np.zeros((0, nfft), complex)
+
+
+def test_stream_frames_match_reference_golden(sp, golden_stream):
+    """spectral.stream_frame == reference _stream_data outputs (streamer.py:119-121)."""
+    z, meta = golden_stream
+    for m in meta:
+        k = m["key"]
+        f, p = sp.stream_frame(z[k + "_samples"], m["sample_rate"], m["center_freq"])
+        assert f.dtype == np.float64 and p.dtype == np.float64 and p.shape == (m["n"],)
+        np.testing.assert_array_equal(f, z[k + "_freqs"])           # integer permutation + exact axis
+        ref = z[k + "_power_db"]
+        P = (10 ** (ref / 20) - 1e-12).clip(min=0) ** 2
+        if np.all(ref == -240.0):
+            assert np.abs(p + 240.0).max() < 1e-3
+        else:
+            parity.check_db_rows(p[None, :], P[None, :], what=k)
+            assert int(np.argmax(p)) == int(np.argmax(ref))
+
+
+@pytest.mark.parametrize("nfft,hop,kind", [(16, 16, "rect"), (32, 8, "hann"), (64, 16, "blackman"), (128, 128, "hann"),
+                                           (256, 64, "hann"), (512, 256, "blackman"), (1024, 512, "hann"),
+                                           (2048, 1024, "hann"), (4096, 1024, "hann"), (4096, 4096, "rect"),
+                                           (8192, 4096, "hann"), (8192, 2048, "blackman")])
+def test_cf32_host_parity(sp, nfft, hop, kind):
+    L = nfft + hop * 37 + 11
+    x = sref.synth_iq(L, seed=nfft + hop).astype(np.complex64)
+    pl = sp.SpectralPlan(nfft, hop, kind)
+    r = pl.stft(x, db_rows=True, wf_rows=True, spectrum=True, welch=True, maxhold=True, vmin=-60.0, vmax=60.0)
+    X = oracle_rows(x, nfft, hop, kind)
+    P = X.real**2 + X.imag**2
+    assert r.n_frames == 38 == X.shape[0]
+    assert np.abs(r.spectrum - X).max() <= 4e-6 * np.sqrt(P.mean())
+    parity.check_db_rows(r.db_rows, P, what=f"N={nfft}")
+    parity.check_power(r.welch_acc[0], P.sum(axis=0), what="welch")
+    parity.check_power(r.maxhold[0], P.max(axis=0), what="maxhold")
+    parity.check_u8(r.wf_rows, sref.amplitude_db(X), -60.0, 60.0, what="u8")
+    assert r.h2d_bytes == L * 8 and r.d2h_bytes > 0
+    pl.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_4096_kernel_variants_agree(sp, variant):
+    n, hop = 4096, 1024
+    x = sref.to_ci16(sref.synth_iq(n + 300 * hop, seed=77))
+    pl = sp.SpectralPlan(n, hop, "hann", sp.FMT_CI16, variant=variant)
+    r = pl.stft(x, db_rows=True, wf_rows=True, welch=True, maxhold=True, vmin=0.0, vmax=130.0)
+    X = oracle_rows(x, n, hop, "hann", fmt=1)
+    P = X.real**2 + X.imag**2
+    parity.check_db_rows(r.db_rows, P, what=f"variant {variant}")
+    parity.check_power(r.welch_acc[0], P.sum(axis=0), what="welch")
+    parity.check_power(r.maxhold[0], P.max(axis=0), what="maxhold")
+    parity.check_u8(r.wf_rows, sref.amplitude_db(X), 0.0, 130.0)
+    pl.close()
+
+
+def test_ci16_scale_sigmf(sp):
+    """SigMF ci16_le autoscale 2^-15 (process_sigmf_data.py:52) vs raw stream values (streamer.py:114)."""
+    n, hop = 1024, 512
+    x = sref.to_ci16(sref.synth_iq(n + 40 * hop, seed=5))
+    for scale in (1.0, 2.0**-15):
+        pl = sp.SpectralPlan(n, hop, "hann", sp.FMT_CI16, in_scale=scale)
+        r = pl.stft(x, db_rows=True, welch=True)
+        X = oracle_rows(x, n, hop, "hann", fmt=1, scale=scale)
+        P = X.real**2 + X.imag**2
+        parity.check_db_rows(r.db_rows, P, what=f"scale {scale}")
+        parity.check_power(r.welch_acc[0], P.sum(axis=0))
+        pl.close()
+
+
+def test_device_resident_equals_host_path(sp):
+    from sdr_iq_visualizer_b200 import _native as nat
+    n, hop = 2048, 512
+    x = sref.synth_iq(n + 500 * hop, seed=9).astype(np.complex64)
+    pl = sp.SpectralPlan(n, hop, "blackman")
+    h = pl.stft(x, db_rows=True, wf_rows=True, welch=True, maxhold=True, vmin=-50, vmax=50)
+    d = pl.stft(nat.DeviceArray.from_host(x), db_rows=True, wf_rows=True, welch=True, maxhold=True, vmin=-50, vmax=50)
+    pl.sync()
+    np.testing.assert_array_equal(h.db_rows, d.db_rows.to_host())
+    np.testing.assert_array_equal(h.wf_rows, d.wf_rows.to_host())
+    np.testing.assert_array_equal(h.maxhold, d.maxhold.to_host())
+    np.testing.assert_allclose(h.welch_acc, d.welch_acc.to_host(), rtol=1e-12)  # fp64 atomics: order may differ
+    pl.close()
+
+
+def test_multistream_and_accumulate(sp):
+    n, hop, S = 2048, 1024, 5
+    L = n + 60 * hop
+    xs = np.concatenate([sref.synth_iq(L, seed=100 + s, snr_db=5.0 * (s + 1)) for s in range(S)]).astype(np.complex64)
+    pl = sp.SpectralPlan(n, hop, "hann")
+    r = pl.stft(xs, n_streams=S, welch=True, maxhold=True, wf_rows=True, vmin=-40, vmax=60)
+    X = oracle_rows(xs, n, hop, "hann", n_streams=S)
+    P = (X.real**2 + X.imag**2).reshape(S, -1, n)
+    assert r.n_frames == 61 and r.wf_rows.shape == (S * 61, n)
+    for s in range(S):
+        parity.check_power(r.welch_acc[s], P[s].sum(axis=0), what=f"stream {s}")
+        parity.check_power(r.maxhold[s], P[s].max(axis=0))
+    parity.check_u8(r.wf_rows, sref.amplitude_db(X), -40, 60)
+    # accumulate=True continues the running Welch sum / max-hold (block-wise streaming use)
+    half = (L // 2 // hop) * hop
+    a = pl.stft(xs[:L][: half + n - hop], welch=True, maxhold=True)
+    b = pl.stft(xs[:L][half:], welch=a.welch_acc, maxhold=a.maxhold, accumulate=True)
+    assert a.n_frames + b.n_frames == 61
+    parity.check_power(b.welch_acc[0], P[0].sum(axis=0), what="accumulated welch")
+    parity.check_power(b.maxhold[0], P[0].max(axis=0), what="accumulated maxhold")
+    pl.close()
+
+
+def test_edge_cases(sp):
+    pl = sp.SpectralPlan(1024, 512, "hann")
+    r = pl.stft(np.zeros(100, np.complex64), db_rows=True, welch=True)   # shorter than one frame
+    assert r.n_frames == 0 and r.db_rows.shape == (0, 1024) and np.all(r.welch_acc == 0)
+    r = pl.stft(np.zeros(0, np.complex64), db_rows=True)
+    assert r.n_frames == 0
+    r = pl.stft(np.zeros(1024, np.complex64), db_rows=True, wf_rows=True)  # exactly one all-zero frame
+    assert r.n_frames == 1 and np.abs(r.db_rows + 240.0).max() < 1e-3 and np.all(r.wf_rows == 0)
+    with pytest.raises(sp.SpectralError):
+        sp.SpectralPlan(1000)          # not a power of two
+    with pytest.raises(sp.SpectralError):
+        sp.SpectralPlan(1024, 2048)    # hop > nfft
+    pl.close()
+    # odd hop (not a divisor of N, frames start at unaligned samples)
+    pl = sp.SpectralPlan(256, 77, "hann")
+    x = sref.synth_iq(5000, seed=1).astype(np.complex64)
+    r = pl.stft(x, db_rows=True)
+    X = oracle_rows(x, 256, 77, "hann")
+    parity.check_db_rows(r.db_rows, X.real**2 + X.imag**2)
+    pl.close()
+
+
+def test_welch_psd_matches_mlab_semantics(sp):
+    """welch_psd == oracle restatement of plt.psd (process_sigmf_data.py:188): first 10 000 samples,
+    NFFT=1024, noverlap=0, Hann."""
+    x = sref.synth_iq(10000, seed=1).astype(np.complex64)
+    f, pxx = sp.welch_psd(x, 1024, 1024, "hann", sample_rate=1e6, center_freq=2.4e9)
+    fo, po = sref.welch_psd(x, 1024, 1024, "hann", 1e6, 2.4e9)
+    np.testing.assert_array_equal(f, fo)
+    parity.check_power(pxx, po, what="welch psd")
+    # shorter than one frame: zero-padded to N like mlab
+    f, pxx = sp.welch_psd(x[:300], 1024, 1024, "hann", 1e6, 0.0)
+    fo, po = sref.welch_psd(x[:300], 1024, 1024, "hann", 1e6, 0.0)
+    parity.check_power(pxx, po, what="zero-padded welch", rel_tol=2e-4)
+
+
+def test_config1_full_size(sp):
+    """BASELINE config 1: 2^20 cf32, N=1024 Hann, 50 % overlap -- full-array parity."""
+    L, n, hop = 1 << 20, 1024, 512
+    x = sref.synth_iq(L, seed=1).astype(np.complex64)
+    pl = sp.SpectralPlan(n, hop, "hann")
+    r = pl.stft(x, db_rows=True, wf_rows=True, welch=True, maxhold=True, vmin=-30.0, vmax=70.0)
+    assert r.n_frames == 2047
+    X = oracle_rows(x, n, hop, "hann")
+    P = X.real**2 + X.imag**2
+    parity.check_db_rows(r.db_rows, P, what="C1")
+    parity.check_power(r.welch_acc[0], P.sum(axis=0), what="C1 welch")
+    parity.check_power(r.maxhold[0], P.max(axis=0), what="C1 maxhold")
+    parity.check_u8(r.wf_rows, sref.amplitude_db(X), -30.0, 70.0, what="C1 u8")
+    pl.close()
+
+
+def test_config2_slice_and_full_size_properties(sp):
+    """BASELINE config 2: int16 @ 61.44 MS/s, N=4096, 75 % overlap.  Oracle parity on a 2^21-sample
+    slice; at the full one-second size, size-independent properties (Parseval, block additivity)."""
+    n, hop = 4096, 1024
+    Ls = 1 << 21
+    xs = sref.to_ci16(sref.synth_iq(Ls, seed=2))
+    pl = sp.SpectralPlan(n, hop, "hann", sp.FMT_CI16)
+    r = pl.stft(xs, db_rows=True, wf_rows=True, welch=True, maxhold=True, vmin=20.0, vmax=130.0)
+    X = oracle_rows(xs, n, hop, "hann", fmt=1)
+    P = X.real**2 + X.imag**2
+    parity.check_db_rows(r.db_rows, P, what="C2 slice")
+    parity.check_power(r.welch_acc[0], P.sum(axis=0), what="C2 welch")
+    parity.check_power(r.maxhold[0], P.max(axis=0), what="C2 maxhold")
+    parity.check_u8(r.wf_rows, sref.amplitude_db(X), 20.0, 130.0, what="C2 u8")
+    # full size: 61.44 M samples (tile the slice; content does not matter for the properties)
+    L = 61_440_000
+    reps = -(-L // Ls)
+    full = np.tile(xs.reshape(-1, 2), (reps, 1))[:L].reshape(-1)
+    rf = pl.stft(full, welch=True, maxhold=True)
+    assert rf.n_frames == 59_997
+    # Parseval per frame summed over frames: sum_k sum_f |X_f[k]|^2 = N * sum_f sum_n |w[n] x_f[n]|^2
+    w = sref.window("hann", n).astype(np.float32).astype(np.float64)
+    iq = full.reshape(-1, 2).astype(np.float64)
+    e = iq[:, 0] ** 2 + iq[:, 1] ** 2
+    # sum over frames of sum_n w^2[n] e[f*hop+n]  via correlation of e with w^2 at stride hop
+    w2 = w * w
+    tot = 0.0
+    for q in range(n // hop):
+        seg = w2[q * hop:(q + 1) * hop]
+        blocks = e[: (L // hop) * hop].reshape(-1, hop) @ seg          # per hop-block energy under this window quarter
+        tot += blocks[q: q + rf.n_frames].sum()
+    assert abs(rf.welch_acc.sum() - n * tot) <= 1e-6 * n * tot
+    # block additivity: two halves with accumulate == one shot
+    cut = (rf.n_frames // 2) * hop
+    a = pl.stft(full[: 2 * (cut + n - hop)], welch=True, maxhold=True)
+    b = pl.stft(full[2 * cut:], welch=a.welch_acc, maxhold=a.maxhold, accumulate=True)
+    assert a.n_frames + b.n_frames == rf.n_frames
+    np.testing.assert_allclose(b.welch_acc, rf.welch_acc, rtol=1e-9)
+    np.testing.assert_array_equal(b.maxhold, rf.maxhold)
+    pl.close()
