@@ -149,6 +149,49 @@ SPX_API int spx_welch_finalize(spx_plan* plan, int32_t mem, const double* welch_
 /* sum(w^2) and sum(w) of the plan's float64 window (in_scale is applied to the data, not counted here) */
 SPX_API int spx_plan_window_sums(spx_plan* plan, double* sum_w2, double* sum_w);
 
+/* ---------------------------------------------------------------- classifier measurements */
+/* What classify_signal_advanced / classify_signal_simple measure on one spectrum
+ * (/root/reference/app/processing/classifier.py:45-58 and :18-23; helpers :163-219).
+ * Bin indices are exact; the host layer turns them into Hz with the caller's `freqs` array and
+ * applies the label rules + temporal smoothing (:60-161). */
+typedef struct {
+    int32_t n;                 /* bins */
+    int32_t argmax;            /* first index of the maximum */
+    double peak_db;            /* np.max(power_db) (:46) */
+    double noise_floor_db;     /* np.percentile(power_db, 20), 'linear' (:181) */
+    double snr_db;             /* peak - noise floor (:46), un-rounded */
+    double adaptive_thr;       /* max(nf + 5, peak - 0.9 snr + 5) (:53) */
+    double p20_lo, p20_hi;     /* the two order statistics the percentile interpolates */
+    int32_t min_distance_bins; /* max(3, n // 300) (:54) */
+    int32_t first_3db, last_3db;   /* first/last bin with p >= peak - 3  (:163-170); -1 if none */
+    int32_t first_10db, last_10db;
+    int32_t first_20db, last_20db;
+    int32_t simple_first, simple_last; /* first/last bin with p > peak - 20 (strict, :18-21) */
+    double flatness;           /* exp(mean(ln p)) / mean(p), p = max(10^(dB/10), 1e-15), clipped to [0,1] (:183-189) */
+    double kurtosis;           /* mean(((x - mu)/sigma)^4), 0 if sigma < 1e-9 (:191-198) */
+    double mean_db, std_db;
+    int32_t n_candidates;      /* strict local maxima above adaptive_thr */
+    int32_t peak_count;        /* after greedy min-distance thinning (:200-212) */
+    double peak_spacing_std_bins; /* population std of successive peak spacings in bins (0 if < 3 peaks) */
+    int32_t peaks_stored;      /* how many peak indices were written to `peaks` */
+    int32_t reserved;
+} spx_features;
+
+/* optional overrides (NULL = the reference's choices: drops 3/10/20 dB, adaptive threshold, auto distance) */
+typedef struct {
+    double drop_db[3];           /* occupied-bandwidth drops reported in first/last_{3,10,20}db */
+    double peak_threshold_db;    /* used when use_peak_threshold != 0 (classifier.py:200 `threshold_db`) */
+    int32_t use_peak_threshold;
+    int32_t min_distance_bins;   /* > 0 overrides max(3, n // 300) */
+} spx_feature_opts;
+
+/* power_db: `batch` spectra of n values (dtype 0 = float32, 1 = float64), spectrum b at b*stride.
+ * out[batch] and peaks[batch][peaks_cap] (optional) are HOST buffers in both memory modes; the call
+ * returns after the results have landed.  n == 0 yields zeroed features ("No Data"). */
+SPX_API int spx_classify_features(int32_t device, int32_t mem, const void* power_db, int32_t dtype, int32_t n,
+                                  int32_t batch, int64_t stride, spx_features* out, int32_t* peaks,
+                                  int32_t peaks_cap, const spx_feature_opts* opts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,22 @@ class spx_stft_args(C.Structure):
                 ("d2h_bytes_out", C.c_int64)]
 
 
+class spx_features(C.Structure):
+    _fields_ = [("n", C.c_int32), ("argmax", C.c_int32), ("peak_db", C.c_double), ("noise_floor_db", C.c_double),
+                ("snr_db", C.c_double), ("adaptive_thr", C.c_double), ("p20_lo", C.c_double), ("p20_hi", C.c_double),
+                ("min_distance_bins", C.c_int32), ("first_3db", C.c_int32), ("last_3db", C.c_int32),
+                ("first_10db", C.c_int32), ("last_10db", C.c_int32), ("first_20db", C.c_int32),
+                ("last_20db", C.c_int32), ("simple_first", C.c_int32), ("simple_last", C.c_int32),
+                ("flatness", C.c_double), ("kurtosis", C.c_double), ("mean_db", C.c_double), ("std_db", C.c_double),
+                ("n_candidates", C.c_int32), ("peak_count", C.c_int32), ("peak_spacing_std_bins", C.c_double),
+                ("peaks_stored", C.c_int32), ("reserved", C.c_int32)]
+
+
+class spx_feature_opts(C.Structure):
+    _fields_ = [("drop_db", C.c_double * 3), ("peak_threshold_db", C.c_double), ("use_peak_threshold", C.c_int32),
+                ("min_distance_bins", C.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/spx.h declares (tests check this)
 _SIGNATURES = {
     "spx_abi_version": (C.c_int, []),
@@ -78,6 +94,9 @@ _SIGNATURES = {
                                 C.POINTER(C.c_float)]),
     "spx_welch_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
+    "spx_classify_features": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                        C.POINTER(spx_features), C.c_void_p, C.c_int32, C.POINTER(spx_feature_opts),
+                                        C.c_void_p]),
     "spx_plan_window_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
