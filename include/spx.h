@@ -192,6 +192,20 @@ SPX_API int spx_classify_features(int32_t device, int32_t mem, const void* power
                                   int32_t batch, int64_t stride, spx_features* out, int32_t* peaks,
                                   int32_t peaks_cap, const spx_feature_opts* opts, void* stream);
 
+/* ---------------------------------------------------------------- time-domain / constellation views */
+/* 2-D I/Q density histogram with np.histogram2d(I, Q, bins, range=[[-R,R],[-R,R]]) semantics
+ * (replaces the 2000-point scatter of app/dashboard/callbacks.py:199-214).
+ * hist is uint32 [bins][bins], H[i][j] with i <-> I, j <-> Q; right edge inclusive, values outside
+ * dropped; samples are multiplied by in_scale first.  accumulate != 0 adds to the existing counts. */
+SPX_API int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_t in_fmt, double in_scale, int64_t n,
+                          double r, int32_t bins, uint32_t* hist, int32_t accumulate, void* stream);
+
+/* per-frame mean and peak of I^2+Q^2 (scripts/pyad-iio-test.py:93 prints the mean per
+ * buffer); frames as in spx_frame_count(n, frame_len, hop); outputs float32 [F] each. */
+SPX_API int spx_frame_stats(int32_t device, int32_t mem, const void* in, int32_t in_fmt, float in_scale, int64_t n,
+                            int32_t frame_len, int32_t hop, float* mean_pow, float* peak_pow, int64_t* n_frames_out,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,6 +224,6 @@ def test_config2_slice_and_full_size_properties(sp):
     a = pl.stft(full[: 2 * (cut + n - hop)], welch=True, maxhold=True)
     b = pl.stft(full[2 * cut:], welch=a.welch_acc, maxhold=a.maxhold, accumulate=True)
     assert a.n_frames + b.n_frames == rf.n_frames
-    np.testing.assert_allclose(b.welch_acc, rf.welch_acc, rtol=1e-9)
+    np.testing.assert_allclose(b.welch_acc, rf.welch_acc, rtol=2e-6)  # fp32 partial sums per <=256-frame chunk
     np.testing.assert_array_equal(b.maxhold, rf.maxhold)
     pl.close()

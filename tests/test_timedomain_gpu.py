@@ -1,0 +1,77 @@
+"""GPU tests of the time-domain views (K4): histogram counts bit-exact vs np.histogram2d, frame stats."""
+import numpy as np
+import pytest
+
+from oracle import spectral_ref as sref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def td():
+    from sdr_iq_visualizer_b200 import timedomain, _native
+    assert _native.device_count() > 0
+    return timedomain
+
+
+@pytest.mark.parametrize("r,bins", [(4.0, 256), (3.3, 256), (1.0, 64), (0.7, 100), (2.5, 1)])
+def test_hist2d_cf32_bit_exact(td, r, bins):
+    x = sref.synth_iq(1 << 18, seed=3).astype(np.complex64)
+    # plant values exactly on edges, on the closed right edge, just outside, and NaN
+    step = 2 * r / bins
+    edges = np.linspace(-r, r, bins + 1)
+    special = np.concatenate([edges, [np.nextafter(r, np.inf), np.nextafter(-r, -np.inf), r, -r, np.nan]]).astype(np.float32)
+    x[: special.size] = special + 1j * special[::-1]
+    h = td.iq_hist2d(x, r, bins)
+    want = sref.iq_hist2d(x, r, bins)
+    assert h.dtype == np.uint32 and h.shape == (bins, bins)
+    np.testing.assert_array_equal(h, want)
+
+
+def test_hist2d_ci16_and_accumulate(td):
+    from sdr_iq_visualizer_b200 import _native as nat
+    raw = sref.to_ci16(sref.synth_iq(1 << 18, seed=4))
+    h = td.iq_hist2d(raw, 2048.0, 256, in_fmt=nat.FMT_CI16)
+    want = sref.iq_hist2d(sref.unpack_ci16(raw), 2048.0, 256)
+    np.testing.assert_array_equal(h, want)
+    # scaled (SigMF ci16 autoscale) and non power-of-two range
+    h2 = td.iq_hist2d(raw, 0.05, 256, in_fmt=nat.FMT_CI16, in_scale=2.0**-15)
+    np.testing.assert_array_equal(h2, sref.iq_hist2d(sref.unpack_ci16(raw, 2.0**-15), 0.05, 256))
+    # accumulate: two halves == whole; device-resident == host
+    a = td.iq_hist2d(raw[: raw.size // 2], 2048.0, 256, in_fmt=nat.FMT_CI16)
+    b = td.iq_hist2d(raw[raw.size // 2:], 2048.0, 256, in_fmt=nat.FMT_CI16, out=a, accumulate=True)
+    np.testing.assert_array_equal(b, want)
+    d = td.iq_hist2d(nat.DeviceArray.from_host(raw), 2048.0, 256, in_fmt=nat.FMT_CI16)
+    nat.device_sync()
+    np.testing.assert_array_equal(d.to_host(), want)
+
+
+def test_config3_full_size(td):
+    """BASELINE config 3: 16 Mi samples, 256x256 histogram (R = 4), 4096-sample frames."""
+    L = 1 << 24
+    x = sref.synth_iq(L, seed=3).astype(np.complex64)
+    h = td.iq_hist2d(x, 4.0, 256)
+    np.testing.assert_array_equal(h, sref.iq_hist2d(x, 4.0, 256))
+    assert int(h.sum()) == L  # nothing falls outside R = 4 for this signal
+    mean, peak = td.frame_stats(x, 4096, 4096)
+    m_ref, p_ref = sref.frame_stats(x, 4096, 4096)
+    assert mean.shape == (4096,)
+    np.testing.assert_allclose(mean, m_ref, rtol=2e-7)
+    np.testing.assert_allclose(peak, p_ref, rtol=2e-7)
+
+
+def test_frame_stats_overlap_and_edges(td):
+    from sdr_iq_visualizer_b200 import _native as nat
+    x = sref.synth_iq(10_000, seed=8).astype(np.complex64)
+    mean, peak = td.frame_stats(x, 1000, 300)
+    m_ref, p_ref = sref.frame_stats(x, 1000, 300)
+    assert mean.shape == m_ref.shape == (31,)
+    np.testing.assert_allclose(mean, m_ref, rtol=2e-7)
+    np.testing.assert_allclose(peak, p_ref, rtol=2e-7)
+    mean, peak = td.frame_stats(x[:10], 1000)   # shorter than a frame
+    assert mean.shape == (0,)
+    raw = sref.to_ci16(x.astype(np.complex128))
+    mean, peak = td.frame_stats(raw, 512, 512, in_fmt=nat.FMT_CI16)
+    m_ref, p_ref = sref.frame_stats(sref.unpack_ci16(raw), 512, 512)
+    np.testing.assert_allclose(mean, m_ref, rtol=2e-7)
+    np.testing.assert_allclose(peak, p_ref, rtol=0)    # integers: exact
