@@ -82,6 +82,7 @@ int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long l
     L.p.welch_acc = welch_acc;
     L.p.maxhold = maxhold;
     L.p.db_eps = pl->cfg.db_eps;
+    L.p.db_pw_min = pl->cfg.db_eps * pl->cfg.db_eps * 1099511627776.0f;  // (2^20 eps)^2
     L.p.q_vmin = vmin;
     L.p.q_scale = 256.0f / (vmax - vmin);
     L.nfft = pl->cfg.nfft;

@@ -9,6 +9,8 @@ int launch_stft_4k(StftLaunch& L) {
         case 2: return launch_stft_n<4096, TW_REG, 2>(L);
         case 3: return launch_stft_n<4096, TW_REG, 3>(L);
         case 4: return launch_stft_n<4096, TW_SMEM, 2>(L);
+        case 5: return launch_stft_n<4096, TW_REG, 2, true>(L);   // TMA-staged input
+        case 6: return launch_stft_n<4096, TW_LDG, 2, true>(L);
         default: return spx_set_error(SPX_E_INVALID, "unknown kernel variant %d for nfft 4096", L.variant);
     }
 }

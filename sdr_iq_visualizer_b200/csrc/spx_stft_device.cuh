@@ -29,6 +29,7 @@ struct StftParams {
     double* welch_acc;           // [n_streams][N]  += sum_f |X|^2   (fftshift order) or nullptr
     float* maxhold;              // [n_streams][N]  max= |X|^2       (fftshift order) or nullptr
     float db_eps;                // 20*log10(|X| + db_eps)
+    float db_pw_min;             // below this |X|^2 the eps term matters and the exact form is evaluated
     float q_vmin, q_scale;       // u8 = sat(floor((db - vmin) * scale)), scale = 256/(vmax-vmin)
     int frames_per_chunk;        // accumulator flush granularity (<= 256)
     int chunks_per_stream;
@@ -95,7 +96,13 @@ SPX_HD unsigned int sat_floor_u8(float q) {
 }
 #define SPX_DB_PER_LOG2 6.02059991327962390427f  // 20*log10(2)
 
-SPX_HD float amp_db(float pw, float eps) { return SPX_DB_PER_LOG2 * fast_log2(fast_sqrt(pw) + eps); }
+// 20*log10(|X| + eps) (streamer.py:121).  For |X|^2 >= pw_min = (2^20 eps)^2 the eps term changes the
+// result by < 1e-5 dB and 10*log10(|X|^2) is evaluated instead (one MUFU instead of two).
+SPX_HD float amp_db(float pw, float eps, float pw_min) {
+    float db = (0.5f * SPX_DB_PER_LOG2) * fast_log2(pw);
+    if (pw < pw_min) db = SPX_DB_PER_LOG2 * fast_log2(fast_sqrt(pw) + eps);
+    return db;
+}
 
 // ------------------------------------------------------------------ per-thread state
 template <bool ACC>
@@ -151,17 +158,40 @@ SPX_HD void load_frame(float2* v, const StftParams& p, long long sample0, int ti
     }
 }
 
+// pass 0 input from the shared-memory staging buffer that a bulk async copy (TMA) filled
+template <int N, int FMT>
+SPX_HD void load_frame_staged(float2* v, const void* stage, const float* win, int tid) {
+    constexpr int T = N / 16;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        if (FMT == FMT_CF32) {
+            v[t] = reinterpret_cast<const float2*>(stage)[tid + t * T];
+        } else {
+            const short2 s = reinterpret_cast<const short2*>(stage)[tid + t * T];
+            v[t] = make_float2((float)s.x, (float)s.y);
+        }
+    }
+    if (win != nullptr) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const float w = ld_keep(win + tid + t * T);
+            v[t].x *= w;
+            v[t].y *= w;
+        }
+    }
+}
+
 template <int N, int S>
 SPX_HD void pass_load_smem(float2* v, int tid, const float2* src) {
-    constexpr int R = plan_radix(N, S), NB = 16 / R, T = N / 16;
+    constexpr int R = plan_radix(N, S), NB = 16 / R, T = N / 16, M = N / R;
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
         const int j = tid + T * u;
+        // pad0(j + t*M) == pad0(j) + t*(M + M/16) because M is a multiple of 16
+        const int j0 = S == 1 ? pad0(j) : j;
+        constexpr int STEP = S == 1 ? M + M / 16 : M;
 #pragma unroll
-        for (int t = 0; t < R; ++t) {
-            const int i = j + t * (N / R);
-            v[u * R + t] = src[S == 1 ? pad0(i) : i];
-        }
+        for (int t = 0; t < R; ++t) v[u * R + t] = src[j0 + t * STEP];
     }
 }
 
@@ -208,12 +238,10 @@ SPX_HD void pass_store_smem(const float2* v, int tid, float2* dst) {
     for (int u = 0; u < NB; ++u) {
         const int j = tid + T * u;
         const int jm = j & (NS - 1);
-        const int base = (j - jm) * R + jm;
+        // S == 0: i = 16 j + t  ->  pad0(i) = 17 j + t
+        const int base = S == 0 ? 17 * j : (j - jm) * R + jm;
 #pragma unroll
-        for (int t = 0; t < R; ++t) {
-            const int i = base + t * NS;
-            dst[S == 0 ? pad0(i) : i] = v[u * R + t];
-        }
+        for (int t = 0; t < R; ++t) dst[base + t * NS] = v[u * R + t];
     }
 }
 
@@ -225,29 +253,50 @@ SPX_HD int out_bin(int tid, int u, int t) {
 }
 
 // ------------------------------------------------------------------ fused epilogue
+// row position (fftshift order, streamer.py:119) of v[u*R + t]:  ((bin + N/2) mod N)
+//   = shift_off(t) + tid + T*u   because N/2 is a multiple of N/R and tid + T*u < N/R
+template <int N>
+SPX_HD constexpr int shift_off(int t) {
+    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S);
+    return (t * (N / R) + N / 2) & (N - 1);
+}
+
 template <int N, bool ACC>
-SPX_HD void epilogue(const float2* v, int tid, const StftParams& p, long long row, StftAcc<ACC>& acc) {
-    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S), NB = 16 / R;
-    float* db_row = p.db_rows ? p.db_rows + row * N : nullptr;
-    unsigned char* wf_row = p.wf_rows ? p.wf_rows + row * N : nullptr;
-    float2* sp_row = p.spec_rows ? p.spec_rows + row * N : nullptr;
+SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, StftAcc<ACC>& acc) {
+    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S), NB = 16 / R, T = N / 16;
+    if (p.spec_rows) {
+        float2* sp = p.spec_rows + row * N + tid;
 #pragma unroll
-    for (int u = 0; u < NB; ++u) {
+        for (int u = 0; u < NB; ++u)
 #pragma unroll
-        for (int t = 0; t < R; ++t) {
-            const float2 x = v[u * R + t];
-            const int pos = (out_bin<N>(tid, u, t) + N / 2) & (N - 1);  // fftshift (streamer.py:119)
-            const float pw = x.x * x.x + x.y * x.y;
-            if (ACC) {
-                acc.sum[u * R + t] += pw;
-                acc.mx[u * R + t] = fmaxf(acc.mx[u * R + t], pw);
-            }
-            if (sp_row) sp_row[pos] = x;
-            if (db_row || wf_row) {
-                const float db = amp_db(pw, p.db_eps);  // 20*log10(|X| + eps)  (streamer.py:121)
-                if (db_row) db_row[pos] = db;
-                if (wf_row) wf_row[pos] = (unsigned char)sat_floor_u8((db - p.q_vmin) * p.q_scale);
-            }
+            for (int t = 0; t < R; ++t) sp[shift_off<N>(t) + T * u] = v[u * R + t];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i].x = v[i].x * v[i].x + v[i].y * v[i].y;  // |X|^2
+    if (ACC) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            acc.sum[i] += v[i].x;
+            acc.mx[i] = fmaxf(acc.mx[i], v[i].x);
+        }
+    }
+    if (p.db_rows || p.wf_rows) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i].y = amp_db(v[i].x, p.db_eps, p.db_pw_min);
+        if (p.db_rows) {
+            float* db = p.db_rows + row * N + tid;
+#pragma unroll
+            for (int u = 0; u < NB; ++u)
+#pragma unroll
+                for (int t = 0; t < R; ++t) db[shift_off<N>(t) + T * u] = v[u * R + t].y;
+        }
+        if (p.wf_rows) {
+            unsigned char* wf = p.wf_rows + row * N + tid;
+#pragma unroll
+            for (int u = 0; u < NB; ++u)
+#pragma unroll
+                for (int t = 0; t < R; ++t)
+                    wf[shift_off<N>(t) + T * u] = (unsigned char)sat_floor_u8((v[u * R + t].y - p.q_vmin) * p.q_scale);
         }
     }
 }
@@ -255,19 +304,21 @@ SPX_HD void epilogue(const float2* v, int tid, const StftParams& p, long long ro
 // what a flush writes: (slot position, value) pairs are produced by the caller with atomics
 template <int N>
 SPX_HD int acc_pos(int tid, int idx) {
-    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S);
-    return (out_bin<N>(tid, idx / R, idx % R) + N / 2) & (N - 1);
+    constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S), T = N / 16;
+    return shift_off<N>(idx % R) + tid + T * (idx / R);
 }
 
 // ------------------------------------------------------------------ one frame, phase by phase
 // phase k (0 <= k < P) = pass k; barriers between phases are the caller's job.
 template <int N, int FMT, bool ACC, int TWM, int S>
 SPX_HD void stft_phase(float2* v, int tid, const StftParams& p, long long sample0, long long row, bool active,
-                       float2* bufA, float2* bufB, const float2* tw, const TwRegs<N>& twr, StftAcc<ACC>& acc) {
+                       float2* bufA, float2* bufB, const float2* tw, const TwRegs<N>& twr, StftAcc<ACC>& acc,
+                       const void* stage = nullptr) {
     constexpr int P = plan_passes(N);
     if (!active) return;
     if constexpr (S == 0) {
-        load_frame<N, FMT>(v, p, sample0, tid);
+        if (stage) load_frame_staged<N, FMT>(v, stage, p.win, tid);
+        else load_frame<N, FMT>(v, p, sample0, tid);
     } else {
         const float2* src = ((S - 1) & 1) ? bufB : bufA;
         pass_load_smem<N, S>(v, tid, src);

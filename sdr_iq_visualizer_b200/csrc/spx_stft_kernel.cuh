@@ -17,40 +17,107 @@ struct StftCfg {
     static constexpr int FPC = (T >= 256) ? 1 : 256 / T;
     static constexpr int THREADS = T * FPC;
     static constexpr int P = plan_passes(N);
-    static constexpr int SLOT_F2 = (P >= 2 ? padded_size(N) : 0) + (P >= 3 ? N : 0);  // float2 per slot
+    static constexpr int BUF_F2 = (P >= 2 ? padded_size(N) : 0) + (P >= 3 ? N : 0);  // exchange buffers per slot
     static constexpr int TW_F2 = plan_tw_size(N);
-    static constexpr bool ALL_R16 = (N == 256 || N == 4096 || N == 65536);
+    static constexpr bool CAN_STAGE = T >= 32;  // one elected lane per slot issues the bulk copy
+    // float2 per slot including the staging area for one raw frame (cf32: N float2, ci16: N/2 float2)
+    __host__ __device__ static constexpr int slot_f2(bool stage, int fmt) { return BUF_F2 + (stage ? (fmt == FMT_CF32 ? N : N / 2) : 0); }
 };
 
+// barrier among the T threads of one slot; slots never wait for each other
 template <int N>
 __device__ __forceinline__ void slot_barrier(int slot) {
     using C = StftCfg<N>;
-    if constexpr (C::FPC > 1 && C::T >= 32) {
+    if constexpr (C::FPC == 1) {
+        __syncthreads();
+    } else if constexpr (C::T >= 32) {
         asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(C::T) : "memory");
     } else {
-        __syncthreads();
+        // several slots share a warp: synchronise exactly this slot's lanes
+        const unsigned lane0 = (threadIdx.x & 31u) & ~(unsigned)(C::T - 1);
+        const unsigned mask = (C::T >= 32 ? 0xffffffffu : ((1u << C::T) - 1u)) << lane0;
+        __syncwarp(mask);
     }
 }
 
-template <int N, int FMT, bool ACC, int TWM, int OCC>
+// ---- mbarrier / bulk-copy (TMA) primitives
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// position of a worker (slot) in its frame sequence: chunks worker, worker + n_workers, ...
+struct FrameCursor {
+    unsigned chunk;
+    int fi, nf;
+    unsigned stream;
+    long long sbase, rbase;  // first sample / first row of the chunk
+    bool valid;
+    __device__ __forceinline__ void seek(const StftParams& p, unsigned c) {
+        chunk = c;
+        valid = (long long)c < p.total_chunks;
+        fi = 0;
+        if (!valid) { nf = 0; stream = 0; sbase = 0; rbase = 0; return; }
+        stream = c / (unsigned)p.chunks_per_stream;
+        const long long f0 = (long long)(c - stream * (unsigned)p.chunks_per_stream) * p.frames_per_chunk;
+        const long long left = p.frames_per_stream - f0;
+        nf = (int)(left < p.frames_per_chunk ? left : p.frames_per_chunk);
+        sbase = (long long)stream * p.stream_stride + f0 * p.hop;
+        rbase = (long long)stream * p.frames_per_stream + f0;
+    }
+    __device__ __forceinline__ long long sample0(const StftParams& p) const { return sbase + (long long)fi * p.hop; }
+    __device__ __forceinline__ long long row() const { return rbase + fi; }
+};
+
+template <int N, int FMT, bool ACC, int TWM, int OCC, bool STAGE>
 __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const StftParams p) {
     using C = StftCfg<N>;
     constexpr int P = C::P;
+    constexpr unsigned FRAME_BYTES = (unsigned)N * (FMT == FMT_CF32 ? 8u : 4u);
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long mbar[STAGE ? C::FPC : 1];
     float2* smem = reinterpret_cast<float2*>(smem_raw);
 
     const int slot = threadIdx.x / C::T;
     const int tid = threadIdx.x - slot * C::T;
-    float2* bufA = smem + slot * C::SLOT_F2;
+    float2* slot_base = smem + slot * C::slot_f2(STAGE, FMT);
+    void* stage = STAGE ? (void*)slot_base : nullptr;
+    float2* bufA = slot_base + (STAGE ? (FMT == FMT_CF32 ? N : N / 2) : 0);
     float2* bufB = bufA + padded_size(N);
 
     const float2* tw = p.tw;
     if constexpr (TWM == TW_SMEM && P > 1) {
-        float2* tws = smem + C::FPC * C::SLOT_F2;
+        float2* tws = smem + C::FPC * C::slot_f2(STAGE, FMT);
         for (int i = threadIdx.x; i < C::TW_F2; i += C::THREADS) tws[i] = __ldg(p.tw + i);
-        __syncthreads();
         tw = tws;
     }
+    if constexpr (STAGE) {
+        if (tid == 0) mbar_init(&mbar[slot], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if constexpr (STAGE || (TWM == TW_SMEM && P > 1)) __syncthreads();
+
     TwRegs<N> twr;
     if constexpr (TWM == TW_REG && P > 1) {
         if constexpr (P > 1) tw_regs_load_pass<N, 1>(twr, tid, p.tw);
@@ -61,56 +128,68 @@ __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const St
     StftAcc<ACC> acc;
     acc.reset();
 
-    const long long worker = (long long)blockIdx.x * C::FPC + slot;
-    const long long n_workers = (long long)gridDim.x * C::FPC;
-    const long long iters = (p.total_chunks + n_workers - 1) / n_workers;
-    const long long F = p.frames_per_stream;
+    const unsigned worker = blockIdx.x * C::FPC + slot;
+    const unsigned n_workers = gridDim.x * C::FPC;
+    const char* in_bytes = reinterpret_cast<const char*>(p.in);
+
+    FrameCursor cur;
+    cur.seek(p, worker);
+    unsigned parity = 0;
+    if constexpr (STAGE) {
+        if (cur.valid && tid == 0) {
+            mbar_expect_tx(&mbar[slot], FRAME_BYTES);
+            bulk_g2s(stage, in_bytes + cur.sample0(p) * (FMT == FMT_CF32 ? 8 : 4), FRAME_BYTES, &mbar[slot]);
+        }
+    }
 
     float2 v[16];
-    for (long long it = 0; it < iters; ++it) {
-        const long long chunk = it * n_workers + worker;
-        const bool chunk_active = chunk < p.total_chunks;
-        const long long stream = chunk_active ? chunk / p.chunks_per_stream : 0;
-        const long long f0 = chunk_active ? (chunk - stream * p.chunks_per_stream) * p.frames_per_chunk : 0;
-        long long nf = F - f0;
-        if (nf > p.frames_per_chunk) nf = p.frames_per_chunk;
-        if (!chunk_active) nf = 0;
-        const long long sbase = stream * p.stream_stride + f0 * p.hop;
-        const long long rbase = stream * F + f0;
+    while (cur.valid) {
+        const long long s0 = cur.sample0(p), row = cur.row();
+        const bool last_in_chunk = cur.fi + 1 == cur.nf;
+        const unsigned this_stream = cur.stream;
+        // where the next frame of this slot lives (same chunk, or the slot's next chunk)
+        FrameCursor nxt = cur;
+        if (!last_in_chunk) nxt.fi = cur.fi + 1;
+        else nxt.seek(p, cur.chunk + n_workers);
 
-        for (int fi = 0; fi < p.frames_per_chunk; ++fi) {
-            const bool a = fi < nf;
-            const long long s0 = sbase + (long long)fi * p.hop;
-            const long long row = rbase + fi;
-            stft_phase<N, FMT, ACC, TWM, 0>(v, tid, p, s0, row, a, bufA, bufB, tw, twr, acc);
-            if constexpr (P > 1) {
-                slot_barrier<N>(slot);
-                stft_phase<N, FMT, ACC, TWM, 1>(v, tid, p, s0, row, a, bufA, bufB, tw, twr, acc);
-            }
-            if constexpr (P > 2) {
-                slot_barrier<N>(slot);
-                stft_phase<N, FMT, ACC, TWM, 2>(v, tid, p, s0, row, a, bufA, bufB, tw, twr, acc);
-            }
-            if constexpr (P > 3) {
-                slot_barrier<N>(slot);
-                stft_phase<N, FMT, ACC, TWM, 3>(v, tid, p, s0, row, a, bufA, bufB, tw, twr, acc);
-            }
-            // the last pass of an even-P plan reads bufA, which the next frame's pass 0 overwrites
-            if constexpr (P > 1 && (P % 2) == 0) slot_barrier<N>(slot);
+        if constexpr (STAGE) {
+            mbar_wait(&mbar[slot], parity);
+            parity ^= 1u;
         }
+        stft_phase<N, FMT, ACC, TWM, 0>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc, stage);
+        if constexpr (P > 1 || STAGE) slot_barrier<N>(slot);
+        if constexpr (STAGE) {
+            // every thread of the slot has read its staged samples: refill the buffer with the next frame
+            if (nxt.valid && tid == 0) {
+                mbar_expect_tx(&mbar[slot], FRAME_BYTES);
+                bulk_g2s(stage, in_bytes + nxt.sample0(p) * (FMT == FMT_CF32 ? 8 : 4), FRAME_BYTES, &mbar[slot]);
+            }
+        }
+        if constexpr (P > 1) stft_phase<N, FMT, ACC, TWM, 1>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc);
+        if constexpr (P > 2) {
+            slot_barrier<N>(slot);
+            stft_phase<N, FMT, ACC, TWM, 2>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc);
+        }
+        if constexpr (P > 3) {
+            slot_barrier<N>(slot);
+            stft_phase<N, FMT, ACC, TWM, 3>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc);
+        }
+        // the last pass of an even-P plan reads bufA, which the next frame's pass 0 overwrites
+        if constexpr (P > 1 && (P % 2) == 0) slot_barrier<N>(slot);
 
         if constexpr (ACC) {
-            if (chunk_active) {
+            if (last_in_chunk) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const long long o = stream * N + acc_pos<N>(tid, i);
+                    const long long o = (long long)this_stream * N + acc_pos<N>(tid, i);
                     if (p.welch_acc) atomicAdd(p.welch_acc + o, (double)acc.sum[i]);
                     // |X|^2 >= 0: IEEE order == unsigned integer order
                     if (p.maxhold) atomicMax(reinterpret_cast<unsigned int*>(p.maxhold) + o, __float_as_uint(acc.mx[i]));
                 }
+                acc.reset();
             }
-            acc.reset();
         }
+        cur = nxt;
     }
 }
 
@@ -125,11 +204,11 @@ struct StftLaunch {
     cudaStream_t stream;
 };
 
-template <int N, int FMT, bool ACC, int TWM, int OCC>
+template <int N, int FMT, bool ACC, int TWM, int OCC, bool STAGE>
 int launch_stft_inst(StftLaunch& L) {
     using C = StftCfg<N>;
-    auto kern = stft_kernel<N, FMT, ACC, TWM, OCC>;
-    size_t smem = (size_t)C::FPC * C::SLOT_F2 * sizeof(float2);
+    auto kern = stft_kernel<N, FMT, ACC, TWM, OCC, STAGE>;
+    size_t smem = (size_t)C::FPC * C::slot_f2(STAGE, FMT) * sizeof(float2);
     if (TWM == TW_SMEM) smem += (size_t)C::TW_F2 * sizeof(float2);
     static int occ_cache[64] = {0};  // per instantiation, per device (benign race: same value)
     int dev = 0;
@@ -164,13 +243,33 @@ int launch_stft_inst(StftLaunch& L) {
     return SPX_OK;
 }
 
-template <int N, int TWM, int OCC>
-int launch_stft_n(StftLaunch& L) {
+// bulk async copies need 16-byte aligned source addresses and sizes: every frame start must be aligned
+inline bool stage_ok(const StftLaunch& L) {
+    const long long elt = L.in_fmt == FMT_CF32 ? 8 : 4;
+    if (((uintptr_t)L.p.in & 15u) != 0) return false;
+    if ((L.p.hop * elt) % 16 != 0) return false;
+    if (L.p.n_streams > 1 && (L.p.stream_stride * elt) % 16 != 0) return false;
+    return true;
+}
+
+template <int N, int TWM, int OCC, bool STAGE>
+int launch_stft_fmt(StftLaunch& L) {
     const bool acc = L.p.welch_acc != nullptr || L.p.maxhold != nullptr;
     if (L.in_fmt == FMT_CF32) {
-        return acc ? launch_stft_inst<N, FMT_CF32, true, TWM, OCC>(L) : launch_stft_inst<N, FMT_CF32, false, TWM, OCC>(L);
+        return acc ? launch_stft_inst<N, FMT_CF32, true, TWM, OCC, STAGE>(L)
+                   : launch_stft_inst<N, FMT_CF32, false, TWM, OCC, STAGE>(L);
     }
-    return acc ? launch_stft_inst<N, FMT_CI16, true, TWM, OCC>(L) : launch_stft_inst<N, FMT_CI16, false, TWM, OCC>(L);
+    return acc ? launch_stft_inst<N, FMT_CI16, true, TWM, OCC, STAGE>(L)
+               : launch_stft_inst<N, FMT_CI16, false, TWM, OCC, STAGE>(L);
+}
+
+// STAGE_WANTED: use the TMA-staged kernel when the input is suitably aligned, else direct loads
+template <int N, int TWM, int OCC, bool STAGE_WANTED = false>
+int launch_stft_n(StftLaunch& L) {
+    if constexpr (STAGE_WANTED && StftCfg<N>::CAN_STAGE) {
+        if (stage_ok(L)) return launch_stft_fmt<N, TWM, OCC, true>(L);
+    }
+    return launch_stft_fmt<N, TWM, OCC, false>(L);
 }
 
 // one translation unit per size group instantiates these

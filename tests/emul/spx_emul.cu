@@ -13,12 +13,22 @@
 
 using namespace spx;
 
+static bool g_staged = false;  // emulate the bulk-copy staging buffer (pass 0 reads shared memory)
+
 template <int N, int FMT, bool ACC, int TWM, int S>
 static void run_phase(std::vector<float2>& v, StftParams& p, long long s0, long long row, float2* A, float2* B,
                       const float2* tw, std::vector<TwRegs<N>>& twr, std::vector<StftAcc<ACC>>& acc) {
     constexpr int T = N / 16;
+    std::vector<unsigned char> stage;
+    const void* st = nullptr;
+    if (S == 0 && g_staged) {
+        const size_t elt = FMT == FMT_CF32 ? 8 : 4;
+        stage.resize((size_t)N * elt);
+        memcpy(stage.data(), (const char*)p.in + (size_t)s0 * elt, stage.size());
+        st = stage.data();
+    }
     for (int tid = 0; tid < T; ++tid)
-        stft_phase<N, FMT, ACC, TWM, S>(&v[(size_t)tid * 16], tid, p, s0, row, true, A, B, tw, twr[tid], acc[tid]);
+        stft_phase<N, FMT, ACC, TWM, S>(&v[(size_t)tid * 16], tid, p, s0, row, true, A, B, tw, twr[tid], acc[tid], st);
 }
 
 template <int N, int FMT, bool ACC, int TWM>
@@ -89,6 +99,7 @@ extern "C" int spx_emul_stft(int nfft, int in_fmt, int tw_mode, const void* in, 
     p.welch_acc = welch_acc;
     p.maxhold = maxhold;
     p.db_eps = db_eps;
+    p.db_pw_min = db_eps * db_eps * 1099511627776.0f;  // (2^20 eps)^2
     p.q_vmin = vmin;
     p.q_scale = 256.0f / (vmax - vmin);
     if (p.frames_per_stream == 0) return 0;
@@ -96,6 +107,8 @@ extern "C" int spx_emul_stft(int nfft, int in_fmt, int tw_mode, const void* in, 
     p.chunks_per_stream = (int)((p.frames_per_stream + frames_per_chunk - 1) / frames_per_chunk);
     p.total_chunks = (long long)p.chunks_per_stream * n_streams;
     const bool acc = welch_acc != nullptr || maxhold != nullptr;
+    g_staged = (tw_mode & 0x10) != 0;
+    tw_mode &= 0xf;
 #define CASE(NN)                                                                  \
     case NN:                                                                      \
         if (tw_mode == TW_REG) {                                                  \
