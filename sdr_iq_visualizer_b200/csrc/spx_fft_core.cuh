@@ -27,8 +27,24 @@
 namespace spx {
 
 // ------------------------------------------------------------------ complex helpers
-SPX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-SPX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract: one packed FADD2 on sm_100a (same rounding as two scalar adds)
+#ifndef SPX_PACKED_F32X2
+#define SPX_PACKED_F32X2 1
+#endif
+SPX_HD float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && SPX_PACKED_F32X2
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+SPX_HD float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && SPX_PACKED_F32X2
+    return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 SPX_HD float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -70,12 +86,13 @@ SPX_HD void dft2(float2& a, float2& b) {
 }
 
 SPX_HD void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
-    float2 t0 = cadd(v0, v2), t1 = csub(v0, v2);
-    float2 t2 = cadd(v1, v3), t3 = csub(v1, v3);
+    const float2 t0 = cadd(v0, v2), t1 = csub(v0, v2);
+    const float2 t2 = cadd(v1, v3);
+    const float2 u3 = make_float2(v1.y - v3.y, v3.x - v1.x);  // -i (v1 - v3), built directly in rotated form
     v0 = cadd(t0, t2);
     v2 = csub(t0, t2);
-    v1 = make_float2(t1.x + t3.y, t1.y - t3.x);  // t1 - i t3
-    v3 = make_float2(t1.x - t3.y, t1.y + t3.x);  // t1 + i t3
+    v1 = cadd(t1, u3);  // t1 - i t3
+    v3 = csub(t1, u3);  // t1 + i t3
 }
 
 template <int R>

@@ -11,6 +11,7 @@ int launch_stft_4k(StftLaunch& L) {
         case 4: return launch_stft_n<4096, TW_SMEM, 2>(L);
         case 5: return launch_stft_n<4096, TW_REG, 2, true>(L);   // TMA-staged input
         case 6: return launch_stft_n<4096, TW_LDG, 2, true>(L);
+        case 7: return launch_stft_n<4096, TW_HYB, 2, true>(L);   // pass-1 twiddles from smem, pass-2 from registers
         default: return spx_set_error(SPX_E_INVALID, "unknown kernel variant %d for nfft 4096", L.variant);
     }
 }

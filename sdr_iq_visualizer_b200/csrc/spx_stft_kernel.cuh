@@ -107,20 +107,21 @@ __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const St
     float2* bufB = bufA + padded_size(N);
 
     const float2* tw = p.tw;
-    if constexpr (TWM == TW_SMEM && P > 1) {
+    constexpr int TW_SMEM_F2 = TWM == TW_SMEM ? C::TW_F2 : (TWM == TW_HYB ? plan_tw_offset(N, 2) : 0);
+    if constexpr (TW_SMEM_F2 > 0 && P > 1) {
         float2* tws = smem + C::FPC * C::slot_f2(STAGE, FMT);
-        for (int i = threadIdx.x; i < C::TW_F2; i += C::THREADS) tws[i] = __ldg(p.tw + i);
+        for (int i = threadIdx.x; i < TW_SMEM_F2; i += C::THREADS) tws[i] = __ldg(p.tw + i);
         tw = tws;
     }
     if constexpr (STAGE) {
         if (tid == 0) mbar_init(&mbar[slot], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if constexpr (STAGE || (TWM == TW_SMEM && P > 1)) __syncthreads();
+    if constexpr (STAGE || (TW_SMEM_F2 > 0 && P > 1)) __syncthreads();
 
     TwRegs<N> twr;
-    if constexpr (TWM == TW_REG && P > 1) {
-        if constexpr (P > 1) tw_regs_load_pass<N, 1>(twr, tid, p.tw);
+    if constexpr ((TWM == TW_REG || TWM == TW_HYB) && P > 1) {
+        if constexpr (P > 1 && TWM == TW_REG) tw_regs_load_pass<N, 1>(twr, tid, p.tw);
         if constexpr (P > 2) tw_regs_load_pass<N, 2>(twr, tid, p.tw);
         if constexpr (P > 3) tw_regs_load_pass<N, 3>(twr, tid, p.tw);
     }
@@ -210,6 +211,7 @@ int launch_stft_inst(StftLaunch& L) {
     auto kern = stft_kernel<N, FMT, ACC, TWM, OCC, STAGE>;
     size_t smem = (size_t)C::FPC * C::slot_f2(STAGE, FMT) * sizeof(float2);
     if (TWM == TW_SMEM) smem += (size_t)C::TW_F2 * sizeof(float2);
+    if (TWM == TW_HYB) smem += (size_t)plan_tw_offset(N, 2) * sizeof(float2);
     static int occ_cache[64] = {0};  // per instantiation, per device (benign race: same value)
     int dev = 0;
     SPX_CUDA(cudaGetDevice(&dev));
