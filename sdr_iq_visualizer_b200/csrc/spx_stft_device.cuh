@@ -98,11 +98,8 @@ SPX_HD unsigned int sat_floor_u8(float q) {
 
 // 20*log10(|X| + eps) (streamer.py:121).  For |X|^2 >= pw_min = (2^20 eps)^2 the eps term changes the
 // result by < 1e-5 dB and 10*log10(|X|^2) is evaluated instead (one MUFU instead of two).
-SPX_HD float amp_db(float pw, float eps, float pw_min) {
-    float db = (0.5f * SPX_DB_PER_LOG2) * fast_log2(pw);
-    if (pw < pw_min) db = SPX_DB_PER_LOG2 * fast_log2(fast_sqrt(pw) + eps);
-    return db;
-}
+SPX_HD float amp_db_fast(float pw) { return (0.5f * SPX_DB_PER_LOG2) * fast_log2(pw); }
+SPX_HD float amp_db_exact(float pw, float eps) { return SPX_DB_PER_LOG2 * fast_log2(fast_sqrt(pw) + eps); }
 
 // ------------------------------------------------------------------ per-thread state
 template <bool ACC>
@@ -159,8 +156,10 @@ SPX_HD void load_frame(float2* v, const StftParams& p, long long sample0, int ti
 }
 
 // pass 0 input from the shared-memory staging buffer that a bulk async copy (TMA) filled
+// `win_half` is the first N/2 entries of the (symmetric) window in shared memory:
+// w[i] = win_half[i] for i < N/2, win_half[N-1-i] otherwise (np.hanning / np.blackman are exactly symmetric)
 template <int N, int FMT>
-SPX_HD void load_frame_staged(float2* v, const void* stage, const float* win, int tid) {
+SPX_HD void load_frame_staged(float2* v, const void* stage, const float* win_half, int tid) {
     constexpr int T = N / 16;
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
@@ -171,10 +170,11 @@ SPX_HD void load_frame_staged(float2* v, const void* stage, const float* win, in
             v[t] = make_float2((float)s.x, (float)s.y);
         }
     }
-    if (win != nullptr) {
+    if (win_half != nullptr) {
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-            const float w = ld_keep(win + tid + t * T);
+            const int i = tid + t * T;
+            const float w = t < 8 ? win_half[i] : win_half[N - 1 - i];
             v[t].x *= w;
             v[t].y *= w;
         }
@@ -281,8 +281,18 @@ SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, Stf
         }
     }
     if (p.db_rows || p.wf_rows) {
+        // smallest of this thread's 16 powers decides (one branch) whether the eps term can matter
+        float m01 = fminf(v[0].x, v[1].x), m23 = fminf(v[2].x, v[3].x), m45 = fminf(v[4].x, v[5].x);
+        float m67 = fminf(v[6].x, v[7].x), m89 = fminf(v[8].x, v[9].x), mab = fminf(v[10].x, v[11].x);
+        float mcd = fminf(v[12].x, v[13].x), mef = fminf(v[14].x, v[15].x);
+        const float pmin = fminf(fminf(fminf(m01, m23), fminf(m45, m67)), fminf(fminf(m89, mab), fminf(mcd, mef)));
+        if (pmin >= p.db_pw_min) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i].y = amp_db(v[i].x, p.db_eps, p.db_pw_min);
+            for (int i = 0; i < 16; ++i) v[i].y = amp_db_fast(v[i].x);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i].y = amp_db_exact(v[i].x, p.db_eps);
+        }
         if (p.db_rows) {
             float* db = p.db_rows + row * N + tid;
 #pragma unroll
@@ -313,11 +323,11 @@ SPX_HD int acc_pos(int tid, int idx) {
 template <int N, int FMT, bool ACC, int TWM, int S>
 SPX_HD void stft_phase(float2* v, int tid, const StftParams& p, long long sample0, long long row, bool active,
                        float2* bufA, float2* bufB, const float2* tw, const TwRegs<N>& twr, StftAcc<ACC>& acc,
-                       const void* stage = nullptr) {
+                       const void* stage = nullptr, const float* win_half = nullptr) {
     constexpr int P = plan_passes(N);
     if (!active) return;
     if constexpr (S == 0) {
-        if (stage) load_frame_staged<N, FMT>(v, stage, p.win, tid);
+        if (stage) load_frame_staged<N, FMT>(v, stage, win_half, tid);
         else load_frame<N, FMT>(v, p, sample0, tid);
     } else {
         const float2* src = ((S - 1) & 1) ? bufB : bufA;

@@ -22,6 +22,8 @@ struct StftCfg {
     static constexpr bool CAN_STAGE = T >= 32;  // one elected lane per slot issues the bulk copy
     // float2 per slot including the staging area for one raw frame (cf32: N float2, ci16: N/2 float2)
     __host__ __device__ static constexpr int slot_f2(bool stage, int fmt) { return BUF_F2 + (stage ? (fmt == FMT_CF32 ? N : N / 2) : 0); }
+    // staged kernels also keep half of the symmetric window in shared memory (N/2 floats = N/4 float2), once per CTA
+    __host__ __device__ static constexpr int win_f2(bool stage) { return stage ? N / 4 : 0; }
 };
 
 // barrier among the T threads of one slot; slots never wait for each other
@@ -42,18 +44,19 @@ __device__ __forceinline__ void slot_barrier(int slot) {
 
 // ---- mbarrier / bulk-copy (TMA) primitives
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// (all take 32-bit shared-window addresses computed once, outside the frame loop)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -62,7 +65,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
+        "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
 }
@@ -107,14 +110,24 @@ __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const St
     float2* bufB = bufA + padded_size(N);
 
     const float2* tw = p.tw;
+    const float* win_half = nullptr;
+    if constexpr (STAGE) {
+        if (p.win != nullptr) {
+            float* wsm = reinterpret_cast<float*>(smem + C::FPC * C::slot_f2(STAGE, FMT));
+            for (int i = threadIdx.x; i < N / 2; i += C::THREADS) wsm[i] = __ldg(p.win + i);
+            win_half = wsm;
+        }
+    }
     constexpr int TW_SMEM_F2 = TWM == TW_SMEM ? C::TW_F2 : (TWM == TW_HYB ? plan_tw_offset(N, 2) : 0);
     if constexpr (TW_SMEM_F2 > 0 && P > 1) {
-        float2* tws = smem + C::FPC * C::slot_f2(STAGE, FMT);
+        float2* tws = smem + C::FPC * C::slot_f2(STAGE, FMT) + C::win_f2(STAGE);
         for (int i = threadIdx.x; i < TW_SMEM_F2; i += C::THREADS) tws[i] = __ldg(p.tw + i);
         tw = tws;
     }
+    const unsigned bar_u32 = smem_u32(&mbar[STAGE ? slot : 0]);
+    const unsigned stage_u32 = smem_u32(slot_base);
     if constexpr (STAGE) {
-        if (tid == 0) mbar_init(&mbar[slot], 1);
+        if (tid == 0) mbar_init(bar_u32, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if constexpr (STAGE || (TW_SMEM_F2 > 0 && P > 1)) __syncthreads();
@@ -138,8 +151,8 @@ __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const St
     unsigned parity = 0;
     if constexpr (STAGE) {
         if (cur.valid && tid == 0) {
-            mbar_expect_tx(&mbar[slot], FRAME_BYTES);
-            bulk_g2s(stage, in_bytes + cur.sample0(p) * (FMT == FMT_CF32 ? 8 : 4), FRAME_BYTES, &mbar[slot]);
+            mbar_expect_tx(bar_u32, FRAME_BYTES);
+            bulk_g2s(stage_u32, in_bytes + cur.sample0(p) * (FMT == FMT_CF32 ? 8 : 4), FRAME_BYTES, bar_u32);
         }
     }
 
@@ -154,16 +167,16 @@ __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const St
         else nxt.seek(p, cur.chunk + n_workers);
 
         if constexpr (STAGE) {
-            mbar_wait(&mbar[slot], parity);
+            mbar_wait(bar_u32, parity);
             parity ^= 1u;
         }
-        stft_phase<N, FMT, ACC, TWM, 0>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc, stage);
+        stft_phase<N, FMT, ACC, TWM, 0>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc, stage, win_half);
         if constexpr (P > 1 || STAGE) slot_barrier<N>(slot);
         if constexpr (STAGE) {
             // every thread of the slot has read its staged samples: refill the buffer with the next frame
             if (nxt.valid && tid == 0) {
-                mbar_expect_tx(&mbar[slot], FRAME_BYTES);
-                bulk_g2s(stage, in_bytes + nxt.sample0(p) * (FMT == FMT_CF32 ? 8 : 4), FRAME_BYTES, &mbar[slot]);
+                mbar_expect_tx(bar_u32, FRAME_BYTES);
+                bulk_g2s(stage_u32, in_bytes + nxt.sample0(p) * (FMT == FMT_CF32 ? 8 : 4), FRAME_BYTES, bar_u32);
             }
         }
         if constexpr (P > 1) stft_phase<N, FMT, ACC, TWM, 1>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc);
@@ -209,7 +222,7 @@ template <int N, int FMT, bool ACC, int TWM, int OCC, bool STAGE>
 int launch_stft_inst(StftLaunch& L) {
     using C = StftCfg<N>;
     auto kern = stft_kernel<N, FMT, ACC, TWM, OCC, STAGE>;
-    size_t smem = (size_t)C::FPC * C::slot_f2(STAGE, FMT) * sizeof(float2);
+    size_t smem = (size_t)(C::FPC * C::slot_f2(STAGE, FMT) + C::win_f2(STAGE)) * sizeof(float2);
     if (TWM == TW_SMEM) smem += (size_t)C::TW_F2 * sizeof(float2);
     if (TWM == TW_HYB) smem += (size_t)plan_tw_offset(N, 2) * sizeof(float2);
     static int occ_cache[64] = {0};  // per instantiation, per device (benign race: same value)

@@ -9,7 +9,7 @@ int launch_stft_small(StftLaunch& L) {
         case 64: return launch_stft_n<64, TW_LDG, 2>(L);
         case 128: return launch_stft_n<128, TW_LDG, 2>(L);
         case 256: return launch_stft_n<256, TW_LDG, 2>(L);
-        case 512: return launch_stft_n<512, TW_LDG, 2>(L);
+        case 512: return launch_stft_n<512, TW_LDG, 2, true>(L);
         default: return spx_set_error(SPX_E_UNSUPPORTED, "nfft %d", L.nfft);
     }
 }

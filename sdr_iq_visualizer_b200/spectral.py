@@ -26,6 +26,7 @@ from ._native import (FMT_CF32, FMT_CI16, MEM_DEVICE, MEM_HOST, WINDOW_BLACKMAN,
 _WINDOWS = {"rect": WINDOW_RECT, "boxcar": WINDOW_RECT, "none": WINDOW_RECT, None: WINDOW_RECT,
             "hann": WINDOW_HANN, "hanning": WINDOW_HANN, "blackman": WINDOW_BLACKMAN}
 
+DEFAULT_VARIANT = {}       # nfft -> kernel tuning variant (0 = library default everywhere)
 DB_EPS_REFERENCE = 1e-12   # streamer.py:121
 DB_EPS_LEGACY = 1e-10      # scripts/sdr_realtime_dash.py:73
 

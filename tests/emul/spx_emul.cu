@@ -28,7 +28,8 @@ static void run_phase(std::vector<float2>& v, StftParams& p, long long s0, long 
         st = stage.data();
     }
     for (int tid = 0; tid < T; ++tid)
-        stft_phase<N, FMT, ACC, TWM, S>(&v[(size_t)tid * 16], tid, p, s0, row, true, A, B, tw, twr[tid], acc[tid], st);
+        stft_phase<N, FMT, ACC, TWM, S>(&v[(size_t)tid * 16], tid, p, s0, row, true, A, B, tw, twr[tid], acc[tid], st,
+                                        st ? p.win : nullptr);  // first N/2 entries of the global table = the half table
 }
 
 template <int N, int FMT, bool ACC, int TWM>

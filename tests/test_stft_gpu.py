@@ -68,7 +68,7 @@ def test_cf32_host_parity(sp, nfft, hop, kind):
     pl.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_4096_kernel_variants_agree(sp, variant):
     n, hop = 4096, 1024
     x = sref.to_ci16(sref.synth_iq(n + 300 * hop, seed=77))
