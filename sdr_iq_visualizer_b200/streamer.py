@@ -1,0 +1,236 @@
+"""SDR data streamer -- drop-in for /root/reference/app/sdr/streamer.py with the spectrum computed
+on the GPU.
+
+Kept from the reference: the ``SDRDataStreamer`` constructor and its
+defaults (streamer.py:8-10), attributes ``uri/sample_rate/center_freq/rx_lo/rx_rf_bandwidth/
+rx_buffer_size/sdr/data_queue/running/thread/connected``, the methods ``connect / is_connected /
+start_streaming / stop_streaming / reconnect / get_status / get_latest_data``, the module global
+``sdr_streamer`` and the result dict of one frame (streamer.py:123-130):
+``{'time','samples','freqs','power_db','sample_rate','center_freq'}`` with ``freqs``/``power_db``
+float64[N] in fftshift order.  ``import adi`` stays at module top so tests can mock it.
+
+Changed on purpose:
+  * the three numpy lines (streamer.py:119-121) are one call into ``spectral.stream_frame`` (CUDA);
+    the frequency axis is cached per (N, fs, fc) instead of being rebuilt per buffer;
+  * a compute failure raises ``SpectralError`` and is logged and counted separately -- it no longer
+    looks like a radio fault and never triggers a reconnect (reference :157-174 would);
+  * ``get_latest_data()`` returns the NEWEST queued frame (the reference pops the oldest, SURVEY.md
+    section 0);
+  * ``get_status()`` also reports compute errors, samples processed and H2D bytes.
+"""
+import logging
+import queue
+import threading
+import time
+
+import adi
+import numpy as np
+
+from . import spectral
+from ._native import SpectralError
+
+logger = logging.getLogger(__name__)
+
+_FATAL_ERRNOS = (9, 10054)        # bad descriptor, connection reset  (streamer.py:137)
+_RECONNECT_ERRNOS = (110, 113)    # timed out, host unreachable       (streamer.py:148)
+
+
+class SDRDataStreamer:
+    def __init__(self, uri="ip:192.168.2.1", sample_rate=1_000_000,
+                 center_freq=2_400_000_000, rx_lo=2_400_000_000,
+                 rx_rf_bandwidth=4_000_000, rx_buffer_size=2**12):
+        self.uri = uri
+        self.sample_rate = sample_rate
+        self.center_freq = center_freq
+        self.rx_lo = rx_lo
+        self.rx_rf_bandwidth = rx_rf_bandwidth
+        self.rx_buffer_size = rx_buffer_size
+        self.sdr = None
+        self.data_queue = queue.Queue(maxsize=100)
+        self.running = False
+        self.thread = None
+        self.connected = False
+        self._reconnect_lock = threading.Lock()
+        self._axis_key = None
+        self._axis = None
+        self.compute_errors = 0
+        self.samples_processed = 0
+        self.h2d_bytes = 0
+
+    # ------------------------------------------------------------------ radio control (host I/O)
+    def connect(self):
+        """Open the Pluto and push the RX configuration; True on success."""
+        try:
+            self.sdr = adi.Pluto(uri=self.uri)
+            self.sdr.sample_rate = int(self.sample_rate)
+            self.sdr.rx_rf_bandwidth = int(self.rx_rf_bandwidth)
+            self.sdr.rx_lo = int(self.rx_lo)
+            self.sdr.rx_buffer_size = self.rx_buffer_size
+            logger.info("Connected to SDR at %s (fs=%s, lo=%s, bw=%s)", self.uri, self.sdr.sample_rate,
+                        self.sdr.rx_lo, self.sdr.rx_rf_bandwidth)
+            self.connected = True
+        except Exception as exc:
+            logger.error("Failed to connect to SDR: %s", exc)
+            self.sdr = None
+            self.connected = False
+        return self.connected
+
+    def is_connected(self):
+        """Cheap check; never touches device properties (that would disturb rx())."""
+        return self.sdr is not None and self.connected
+
+    def start_streaming(self):
+        if not self.sdr:
+            logger.error("SDR not connected")
+            return False
+        self.running = True
+        self.thread = threading.Thread(target=self._stream_data, daemon=True)
+        self.thread.start()
+        return True
+
+    def stop_streaming(self):
+        self.running = False
+        if self.thread:
+            self.thread.join(timeout=1)
+        logger.info("Stopped SDR data streaming")
+
+    def reconnect(self):
+        logger.info("Attempting to reconnect to SDR...")
+        self.sdr = None
+        return self.connect()
+
+    def _attempt_reconnect(self, max_attempts=5, base_delay=0.5):
+        """Exponential-backoff reconnect under a lock; True on success."""
+        with self._reconnect_lock:
+            for attempt in range(1, max_attempts + 1):
+                if self.reconnect():
+                    logger.info("Auto-reconnect succeeded on attempt %d.", attempt)
+                    return True
+                time.sleep(min(base_delay * (2 ** (attempt - 1)), 5.0))
+        return False
+
+    # ------------------------------------------------------------------ the hot path
+    def _frequency_axis(self, n):
+        key = (n, self.sample_rate, self.center_freq)
+        if key != self._axis_key:
+            self._axis = spectral.freq_axis(n, self.sample_rate, self.center_freq)
+            self._axis_key = key
+        return self._axis
+
+    def process_buffer(self, samples):
+        """One rx buffer -> the frame dict of streamer.py:123-130 (spectrum on the GPU)."""
+        n = len(samples)
+        _, power_db = spectral.stream_frame(samples, self.sample_rate, self.center_freq)
+        self.samples_processed += n
+        self.h2d_bytes += n * 8
+        return {
+            'time': time.time(),
+            'samples': samples,
+            'freqs': self._frequency_axis(n),
+            'power_db': power_db,
+            'sample_rate': self.sample_rate,
+            'center_freq': self.center_freq,
+        }
+
+    def _stream_data(self):
+        """Read buffers until stopped; radio errors back off / reconnect, compute errors do not."""
+        radio_errors = 0
+        backoff, max_backoff = 0.1, 1.6
+        self.last_success_ts = None
+        self.total_frames = 0
+
+        def recovered(attempts, delay):
+            nonlocal radio_errors, backoff
+            if self._attempt_reconnect(max_attempts=attempts, base_delay=delay):
+                radio_errors, backoff = 0, 0.1
+                return True
+            return False
+
+        while self.running:
+            if not self.is_connected():
+                logger.warning("SDR not connected; trying auto-reconnect before stopping...")
+                if not recovered(5, 0.5):
+                    logger.error("Auto-reconnect failed; stopping stream.")
+                    self.running = False
+                    break
+            try:
+                samples = self.sdr.rx()  # blocking hardware read
+                radio_errors, backoff = 0, 0.1
+                try:
+                    frame = self.process_buffer(samples)
+                except SpectralError as exc:
+                    self.compute_errors += 1
+                    logger.error("GPU spectrum failed (not a radio fault): %s", exc)
+                    continue
+                self._push(frame)
+                self.last_success_ts = frame['time']
+                self.total_frames += 1
+            except OSError as exc:
+                radio_errors += 1
+                err = getattr(exc, 'errno', None)
+                if err in _FATAL_ERRNOS:
+                    logger.error("Fatal OS error errno=%s; attempting auto-reconnect.", err)
+                    self.connected = False
+                    if recovered(5, 0.5):
+                        continue
+                    logger.error("Auto-reconnect failed after fatal error; stopping stream.")
+                    self.running = False
+                    break
+                logger.error("Non-fatal OS error reading SDR (errno=%s): %s", err, exc)
+                if err in _RECONNECT_ERRNOS and recovered(3, 0.2):
+                    continue
+            except Exception as exc:
+                radio_errors += 1
+                logger.error("Error reading SDR data: %s", exc)
+
+            if radio_errors:
+                backoff = min(backoff * 2, max_backoff)
+                logger.warning("Read error #%d; backoff %.2fs", radio_errors, backoff)
+                time.sleep(backoff)
+                if radio_errors >= 3:
+                    logger.warning("Too many consecutive errors; attempting auto-reconnect.")
+                    self.connected = False
+                    if recovered(5, 0.5):
+                        continue
+                    logger.error("Auto-reconnect failed after repeated errors; stopping stream.")
+                    self.running = False
+                    break
+
+    # ------------------------------------------------------------------ queue + status
+    def get_status(self):
+        last = getattr(self, 'last_success_ts', None)
+        return {
+            'connected': self.connected,
+            'running': self.running,
+            'queue_size': self.data_queue.qsize(),
+            'last_success_age_ms': (time.time() - last) * 1000 if last else None,
+            'total_frames': getattr(self, 'total_frames', 0),
+            'compute_errors': self.compute_errors,
+            'samples_processed': self.samples_processed,
+            'h2d_bytes': self.h2d_bytes,
+        }
+
+    def _push(self, data):
+        """Bounded queue, drop-oldest when full (streamer.py:186-194)."""
+        while True:
+            try:
+                self.data_queue.put_nowait(data)
+                return
+            except queue.Full:
+                try:
+                    self.data_queue.get_nowait()
+                except queue.Empty:
+                    return
+
+    def get_latest_data(self):
+        """Newest queued frame or None (older frames are discarded)."""
+        latest = None
+        while True:
+            try:
+                latest = self.data_queue.get_nowait()
+            except queue.Empty:
+                return latest
+
+
+# Shared global instance (streamer.py:203)
+sdr_streamer = SDRDataStreamer()

@@ -1,0 +1,106 @@
+"""CPU tests of the drop-in boundary: the reference's own mock-based streamer tests run against OUR
+`app.sdr.streamer`, the C ABI exports every symbol include/spx.h declares, and the product fails
+loudly without a GPU (no CPU fallback)."""
+import os
+import re
+import subprocess
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def test_abi_exports_every_declared_symbol():
+    from sdr_iq_visualizer_b200 import _native as nat
+    hdr = open(os.path.join(ROOT, "include", "spx.h")).read()
+    declared = set(re.findall(r"SPX_API\s+[\w\s\*]+?\b(spx_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = nat.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"libspx.so does not export {name}"
+    assert declared == set(nat._SIGNATURES), declared ^ set(nat._SIGNATURES)
+    assert lib.spx_abi_version() == 1
+    assert lib.spx_frame_count(61_440_000, 4096, 1024) == 59_997
+
+
+def test_no_cpu_fallback_without_gpu():
+    from sdr_iq_visualizer_b200 import _native as nat
+    if nat.device_count() > 0:
+        pytest.skip("a GPU is present")
+    from sdr_iq_visualizer_b200 import classifier, spectral, timedomain
+    with pytest.raises(nat.SpectralError):
+        spectral.SpectralPlan(1024)
+    with pytest.raises(nat.SpectralError):
+        spectral.stream_frame(np.zeros(64, complex), 1e6, 0.0)
+    with pytest.raises(nat.SpectralError):
+        classifier.classify_signal_advanced(np.arange(8.0), np.zeros(8))
+    with pytest.raises(nat.SpectralError):
+        timedomain.iq_hist2d(np.zeros(8, np.complex64), 1.0)
+    # empty input never reaches the device and answers like the reference (classifier.py:16-17,41-42)
+    assert classifier.classify_signal_simple(np.array([]), np.array([])) == "No Data"
+    assert classifier.classify_signal_advanced(np.array([]), np.array([]))["label"] == "No Data"
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sdr_iq_visualizer_b200")
+    for base in (pkg, os.path.join(ROOT, "app")):
+        for dirpath, _, files in os.walk(base):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert "oracle" not in text.replace("oracle's", ""), f"{f} mentions the oracle"
+
+
+def test_streamer_drop_in_surface():
+    sys.modules.setdefault("adi", MagicMock())
+    from app.sdr.streamer import SDRDataStreamer, sdr_streamer
+    s = SDRDataStreamer()
+    assert (s.uri, s.sample_rate, s.center_freq, s.rx_lo, s.rx_rf_bandwidth, s.rx_buffer_size) == \
+        ("ip:192.168.2.1", 1_000_000, 2_400_000_000, 2_400_000_000, 4_000_000, 4096)
+    assert s.sdr is None and s.running is False and s.thread is None and s.connected is False
+    assert isinstance(sdr_streamer, SDRDataStreamer)
+    for i in range(130):                       # drop-oldest bounded queue
+        s._push({"i": i})
+    assert s.data_queue.qsize() == 100
+    assert s.get_latest_data() == {"i": 129} and s.get_latest_data() is None
+    st = s.get_status()
+    assert {"connected", "running", "queue_size", "last_success_age_ms", "total_frames"} <= set(st)
+
+
+def test_streamer_compute_error_is_not_a_radio_fault(monkeypatch):
+    """SpectralError inside the loop must not count toward the reconnect logic."""
+    sys.modules.setdefault("adi", MagicMock())
+    from sdr_iq_visualizer_b200 import streamer as st
+    s = st.SDRDataStreamer()
+    calls = {"n": 0}
+
+    class Radio:
+        def rx(self_inner):
+            calls["n"] += 1
+            if calls["n"] >= 5:
+                s.running = False
+            return np.zeros(64, complex)
+
+    def boom(*a, **k):
+        raise st.SpectralError(-2, "injected")
+
+    monkeypatch.setattr(st.spectral, "stream_frame", boom)
+    monkeypatch.setattr(s, "_attempt_reconnect", lambda *a, **k: pytest.fail("reconnect attempted"))
+    s.sdr, s.connected, s.running = Radio(), True, True
+    s._stream_data()
+    assert s.compute_errors == 5 and s.total_frames == 0 and s.connected is True
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_streamer_suite_passes_on_drop_in():
+    """Run the reference's tests/test_streamer.py unchanged with `app` resolving to this repo."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider",
+                          os.path.join(REF, "tests", "test_streamer.py"), "--rootdir", ROOT],
+                         cwd=ROOT, env=env, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "6 passed" in res.stdout
