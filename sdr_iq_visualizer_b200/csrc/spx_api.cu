@@ -67,6 +67,17 @@ int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long l
                        float* db_rows, unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold,
                        float vmin, float vmax, cudaStream_t st) {
     if (frames <= 0 || n_streams <= 0) return SPX_OK;
+    if (pl->cfg.nfft >= 16384) {  // four-step path, one stream at a time
+        const size_t elt = pl->cfg.in_fmt == SPX_FMT_CI16 ? 4 : 8;
+        const size_t N = (size_t)pl->cfg.nfft;
+        for (long long s = 0; s < n_streams; ++s) {
+            const size_t r0 = (size_t)(s * frames);
+            SPX_TRY(bigfft_launch_stream(pl, (const char*)in + (size_t)(s * stream_stride) * elt, frames, (long long)r0,
+                                         db_rows, wf_rows, spec_rows, welch_acc ? welch_acc + s * N : nullptr,
+                                         maxhold ? maxhold + s * N : nullptr, vmin, vmax, st));
+        }
+        return SPX_OK;
+    }
     StftLaunch L;
     memset(&L, 0, sizeof(L));
     L.p.in = in;
@@ -348,7 +359,9 @@ int spx_plan_create(spx_plan** out, const spx_plan_config* cfg) {
             if ((e = cudaMalloc(&pl->d_win, wf.size() * sizeof(float))) != cudaSuccess) { rc = spx_set_error(SPX_E_NOMEM, "%s", cudaGetErrorString(e)); break; }
             if ((e = cudaMemcpy(pl->d_win, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = spx_set_error(SPX_E_CUDA, "%s", cudaGetErrorString(e)); break; }
         }
-        if (cfg->nfft <= 8192) {
+        if (cfg->nfft > 8192) {
+            if ((rc = bigfft_plan_init(pl)) != SPX_OK) break;
+        } else {
             std::vector<float2> tw = build_twiddles(cfg->nfft);
             if ((e = cudaMalloc(&pl->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { rc = spx_set_error(SPX_E_NOMEM, "%s", cudaGetErrorString(e)); break; }
             if ((e = cudaMemcpy(pl->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = spx_set_error(SPX_E_CUDA, "%s", cudaGetErrorString(e)); break; }
@@ -374,6 +387,8 @@ int spx_plan_destroy(spx_plan* pl) {
     for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
     if (pl->d_win) cudaFree(pl->d_win);
     if (pl->d_tw) cudaFree(pl->d_tw);
+    if (pl->d_big_tw) cudaFree(pl->d_big_tw);
+    pl->st_big.release();
     pl->st_in.release(); pl->st_db.release(); pl->st_wf.release(); pl->st_spec.release();
     pl->st_welch.release(); pl->st_max.release(); pl->st_misc.release(); pl->st_flush.release();
     delete pl;

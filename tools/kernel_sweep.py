@@ -69,6 +69,9 @@ def main():
         run_case("cf32 hop=N u8", 4096, 4096, "hann", sp.FMT_CF32, L, ["u8"], v)
         run_case("cf32 hop=N acc only", 4096, 4096, "hann", sp.FMT_CF32, L, ["acc"], v)
         run_case("cf32 50% f32", 4096, 2048, "hann", sp.FMT_CF32, L, ["db"], v)
+    for n in (65536, 16384, 1 << 18):
+        run_case(f"cf32 N={n} 50% u8+acc (C5 shape)", n, n // 2, "hann", sp.FMT_CF32, 1 << 26, ["u8", "acc"], 0, iters=5)
+        run_case(f"cf32 N={n} hop=N f32", n, n, "hann", sp.FMT_CF32, 1 << 26, ["db"], 0, iters=5)
     for n in (256, 1024, 2048, 8192):
         run_case(f"cf32 N={n} 50% u8+acc", n, n // 2, "hann", sp.FMT_CF32, L, ["u8", "acc"], 0)
         run_case(f"cf32 N={n} hop=N f32", n, n, "hann", sp.FMT_CF32, L, ["db"], 0)
