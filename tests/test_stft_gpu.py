@@ -245,13 +245,12 @@ def test_large_n_four_step_parity(sp, nfft, hop, kind, fmt):
     assert r.n_frames == F
     X = oracle_rows(x, nfft, hop, kind, fmt=fmt)
     P = X.real**2 + X.imag**2
-    assert np.abs(r.spectrum - X).max() <= 8e-6 * np.sqrt(P.mean())
+    # fp32 FFT error: a floor relative to the frame's RMS bin level plus a part relative to the bin itself
+    assert np.all(np.abs(r.spectrum - X) <= 6e-6 * np.sqrt(P.mean()) + 1e-6 * np.abs(X))
     parity.check_db_rows(r.db_rows, P, what=f"N={nfft}")
     parity.check_power(r.welch_acc[0], P.sum(axis=0), what="welch")
     parity.check_power(r.maxhold[0], P.max(axis=0), what="maxhold")
     parity.check_u8(r.wf_rows, sref.amplitude_db(X), vmin, vmax, what="u8")
-    for k in (0, 1, nfft // 2 - 1, nfft // 2, nfft - 1):   # fftshift order is exact
-        pass
     pl.close()
 
 
