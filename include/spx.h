@@ -43,6 +43,7 @@ extern "C" {
 #define SPX_E_NOMEM (-3)       /* allocation failed */
 #define SPX_E_UNSUPPORTED (-4) /* e.g. nfft not a power of two in [16, 1048576] */
 #define SPX_E_NODEVICE (-5)    /* no CUDA device: there is NO CPU fallback */
+#define SPX_E_BUSY (-6)        /* ring full / nothing to collect */
 
 /* enums */
 #define SPX_WINDOW_RECT 0     /* streamer.py:119 (no window) */
@@ -205,6 +206,53 @@ SPX_API int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_t i
 SPX_API int spx_frame_stats(int32_t device, int32_t mem, const void* in, int32_t in_fmt, float in_scale, int64_t n,
                             int32_t frame_len, int32_t hop, float* mean_pow, float* peak_pow, int64_t* n_frames_out,
                             void* stream);
+
+/* ---------------------------------------------------------------- streaming ingest: pinned ring */
+/* Replaces the reference's queue of per-buffer dicts (app/sdr/streamer.py:18,123-131,186-200) for
+ * high-rate ingest: the producer fills page-locked slots in place; spx_ring_commit enqueues
+ * H2D -> fused STFT -> D2H on three streams and returns at once, so copies of slot k+1 overlap the
+ * kernel of slot k.  Frames run continuously across slots (the unconsumed tail is carried on the device).
+ * Every slot is one Welch / max-hold block.  The ring borrows the plan (keep it alive, same thread rules). */
+typedef struct spx_ring spx_ring;
+
+typedef struct {
+    uint32_t struct_size;
+    int32_t n_slots;        /* 2 .. 64 */
+    int64_t slot_samples;   /* capacity of one slot, >= nfft */
+    int32_t want_wf_rows, want_db_rows, want_welch, want_maxhold;
+    float vmin, vmax;
+} spx_ring_config;
+
+typedef struct {
+    uint32_t struct_size;
+    int32_t reserved;
+    int64_t seq;            /* commit sequence number of this slot */
+    int64_t n_frames;       /* frames completed by this slot */
+    int64_t first_frame;    /* global index of its first frame */
+    const uint8_t* wf_rows; /* pinned host, [n_frames][nfft] (NULL if not requested) */
+    const float* db_rows;
+    const double* welch_acc;
+    const float* maxhold;
+    int64_t h2d_bytes, d2h_bytes; /* bytes this slot moved over PCIe, each direction */
+} spx_ring_result;
+
+typedef struct {
+    uint32_t struct_size;
+    int32_t in_flight;
+    int64_t h2d_bytes, d2h_bytes, samples, frames; /* totals since creation */
+    int64_t reserved;
+} spx_ring_stats_t;
+
+SPX_API int spx_ring_create(spx_ring** out, spx_plan* plan, const spx_ring_config* cfg);
+SPX_API int spx_ring_destroy(spx_ring* ring);
+/* next pinned slot to fill; SPX_E_BUSY when all slots are in flight / unreleased */
+SPX_API int spx_ring_acquire(spx_ring* ring, void** host_slot, int64_t* capacity_samples);
+/* the acquired slot now holds n_samples samples: enqueue its copies and kernel (does not block) */
+SPX_API int spx_ring_commit(spx_ring* ring, int64_t n_samples);
+/* wait for the oldest committed slot and expose its (pinned) results; they stay valid until release */
+SPX_API int spx_ring_collect(spx_ring* ring, spx_ring_result* out);
+SPX_API int spx_ring_release(spx_ring* ring);
+SPX_API int spx_ring_stats(spx_ring* ring, spx_ring_stats_t* out);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libspx.so")
 
-OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_NODEVICE = 0, -1, -2, -3, -4, -5
+OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_NODEVICE, E_BUSY = 0, -1, -2, -3, -4, -5, -6
 WINDOW_RECT, WINDOW_HANN, WINDOW_BLACKMAN = 0, 1, 2
 FMT_CF32, FMT_CI16 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -64,6 +64,23 @@ class spx_features(C.Structure):
                 ("peaks_stored", C.c_int32), ("reserved", C.c_int32)]
 
 
+class spx_ring_config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_slots", C.c_int32), ("slot_samples", C.c_int64),
+                ("want_wf_rows", C.c_int32), ("want_db_rows", C.c_int32), ("want_welch", C.c_int32),
+                ("want_maxhold", C.c_int32), ("vmin", C.c_float), ("vmax", C.c_float)]
+
+
+class spx_ring_result(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_int32), ("seq", C.c_int64), ("n_frames", C.c_int64),
+                ("first_frame", C.c_int64), ("wf_rows", C.c_void_p), ("db_rows", C.c_void_p), ("welch_acc", C.c_void_p),
+                ("maxhold", C.c_void_p), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+class spx_ring_stats_t(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("in_flight", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("samples", C.c_int64), ("frames", C.c_int64), ("reserved", C.c_int64)]
+
+
 class spx_feature_opts(C.Structure):
     _fields_ = [("drop_db", C.c_double * 3), ("peak_threshold_db", C.c_double), ("use_peak_threshold", C.c_int32),
                 ("min_distance_bins", C.c_int32)]
@@ -101,6 +118,13 @@ _SIGNATURES = {
                                 C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "spx_frame_stats": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int64, C.c_int32,
                                   C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "spx_ring_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(spx_ring_config)]),
+    "spx_ring_destroy": (C.c_int, [C.c_void_p]),
+    "spx_ring_acquire": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "spx_ring_commit": (C.c_int, [C.c_void_p, C.c_int64]),
+    "spx_ring_collect": (C.c_int, [C.c_void_p, C.POINTER(spx_ring_result)]),
+    "spx_ring_release": (C.c_int, [C.c_void_p]),
+    "spx_ring_stats": (C.c_int, [C.c_void_p, C.POINTER(spx_ring_stats_t)]),
     "spx_plan_window_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -163,17 +163,31 @@ features_kernel(const T* __restrict__ data, int n, long long stride, spx_feature
             if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)(k >> shift) & 0xffu], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned int r = s_rank, cum = 0u;
-            int d = 0;
-            for (; d < 256; ++d) {
-                const unsigned int h = hist[d];
-                if (r < cum + h) break;
-                cum += h;
+        if (tid < 32) {
+            // warp-parallel search of the digit that contains rank r: 8 bins per lane + shuffle scan
+            const unsigned int r = s_rank;
+            unsigned int h[8], mine = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { h[q] = hist[tid * 8 + q]; mine += h[q]; }
+            unsigned int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
             }
-            s_rank = r - cum;
-            s_cnt_eq = hist[d];
-            s_prefix = prefix | ((unsigned long long)d << shift);
+            const unsigned int excl = incl - mine;
+            const bool here = r >= excl && r < incl;   // exactly one lane (total count > r)
+            if (here) {
+                unsigned int cum = excl;
+                int q = 0;
+                for (; q < 7; ++q) {
+                    if (r < cum + h[q]) break;
+                    cum += h[q];
+                }
+                s_rank = r - cum;
+                s_cnt_eq = h[q];
+                s_prefix = prefix | ((unsigned long long)(tid * 8 + q) << shift);
+            }
         }
         mask |= 0xffull << shift;
         __syncthreads();

@@ -1,0 +1,238 @@
+// spx_ring.cu -- pinned host ring buffer with multi-buffered async ingest (north_star: "app/sdr gains a
+// pinned host ring buffer with double-buffered cudaMemcpyAsync, and H2D bytes are reported separately").
+//
+// Replaces the reference's frame queue of per-buffer dicts (/root/reference/app/sdr/streamer.py:18,
+// 123-131,186-200): the producer writes raw samples straight into a page-locked slot, commit() enqueues
+// H2D (copy stream) -> fused STFT kernel (compute stream) -> D2H of the slot's results (drain stream),
+// and returns immediately; the next slot can be filled while the previous ones are in flight.
+// The stream is continuous across slots: the (N - hop)-sample tail that the next frames still need is
+// carried device-to-device into the head of the next slot's device buffer, never re-sent over PCIe.
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "spx_plan.h"
+
+namespace spx {
+
+struct RingSlot {
+    void* h_in = nullptr;            // pinned, slot_samples * elt
+    char* d_in = nullptr;            // device, (nfft + slot_samples) * elt : [carry][new samples]
+    unsigned char *d_wf = nullptr, *h_wf = nullptr;
+    float *d_db = nullptr, *h_db = nullptr;
+    double *d_welch = nullptr, *h_welch = nullptr;
+    float *d_max = nullptr, *h_max = nullptr;
+    cudaEvent_t e_h2d = nullptr, e_kernel = nullptr, e_done = nullptr;
+    long long seq = -1, n_frames = 0, first_frame = 0, h2d_bytes = 0, d2h_bytes = 0;
+    int state = 0;                   // 0 free, 1 acquired (being filled), 2 committed (in flight / ready)
+};
+
+}  // namespace spx
+
+struct spx_ring {
+    spx_plan* plan = nullptr;
+    spx_ring_config cfg{};
+    std::vector<spx::RingSlot> slots;
+    size_t elt = 8;
+    long long frames_max = 0;
+    int head = 0;                    // next slot to acquire
+    int tail = 0;                    // oldest committed slot not yet released
+    int in_flight = 0;
+    long long seq = 0;
+    long long carry = 0;             // samples already on the device that the next frames start in
+    long long frames_total = 0, samples_total = 0, h2d_total = 0, d2h_total = 0;
+    std::mutex mu;
+};
+
+using namespace spx;
+
+static void ring_free(spx_ring* r) {
+    for (RingSlot& s : r->slots) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_wf) cudaFree(s.d_wf);
+        if (s.h_wf) cudaFreeHost(s.h_wf);
+        if (s.d_db) cudaFree(s.d_db);
+        if (s.h_db) cudaFreeHost(s.h_db);
+        if (s.d_welch) cudaFree(s.d_welch);
+        if (s.h_welch) cudaFreeHost(s.h_welch);
+        if (s.d_max) cudaFree(s.d_max);
+        if (s.h_max) cudaFreeHost(s.h_max);
+        if (s.e_h2d) cudaEventDestroy(s.e_h2d);
+        if (s.e_kernel) cudaEventDestroy(s.e_kernel);
+        if (s.e_done) cudaEventDestroy(s.e_done);
+    }
+    delete r;
+}
+
+extern "C" int spx_ring_create(spx_ring** out, spx_plan* plan, const spx_ring_config* cfg) {
+    if (!out || !plan || !cfg) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(spx_ring_config)) return spx_set_error(SPX_E_INVALID, "spx_ring_config.struct_size mismatch");
+    if (cfg->n_slots < 2 || cfg->n_slots > 64) return spx_set_error(SPX_E_INVALID, "n_slots must be in [2, 64]");
+    if (cfg->slot_samples < plan->cfg.nfft) return spx_set_error(SPX_E_INVALID, "slot_samples must be >= nfft");
+    if (cfg->want_wf_rows && !(cfg->vmax > cfg->vmin)) return spx_set_error(SPX_E_INVALID, "wf rows need vmax > vmin");
+    SPX_CUDA(cudaSetDevice(plan->cfg.device));
+    spx_ring* r = new (std::nothrow) spx_ring();
+    if (!r) return spx_set_error(SPX_E_NOMEM, "out of host memory");
+    r->plan = plan;
+    r->cfg = *cfg;
+    r->elt = plan->cfg.in_fmt == SPX_FMT_CI16 ? 4 : 8;
+    const size_t N = (size_t)plan->cfg.nfft;
+    r->frames_max = (cfg->slot_samples + (long long)N) / plan->cfg.hop + 1;
+    r->slots.resize((size_t)cfg->n_slots);
+    cudaError_t e = cudaSuccess;
+    for (RingSlot& s : r->slots) {
+        const size_t rows = (size_t)r->frames_max * N;
+        if ((e = cudaHostAlloc(&s.h_in, (size_t)cfg->slot_samples * r->elt, cudaHostAllocPortable)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void**)&s.d_in, (N + (size_t)cfg->slot_samples) * r->elt)) != cudaSuccess) break;
+        if (cfg->want_wf_rows) {
+            if ((e = cudaMalloc((void**)&s.d_wf, rows)) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&s.h_wf, rows, cudaHostAllocPortable)) != cudaSuccess) break;
+        }
+        if (cfg->want_db_rows) {
+            if ((e = cudaMalloc((void**)&s.d_db, rows * sizeof(float))) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&s.h_db, rows * sizeof(float), cudaHostAllocPortable)) != cudaSuccess) break;
+        }
+        if (cfg->want_welch) {
+            if ((e = cudaMalloc((void**)&s.d_welch, N * sizeof(double))) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&s.h_welch, N * sizeof(double), cudaHostAllocPortable)) != cudaSuccess) break;
+        }
+        if (cfg->want_maxhold) {
+            if ((e = cudaMalloc((void**)&s.d_max, N * sizeof(float))) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&s.h_max, N * sizeof(float), cudaHostAllocPortable)) != cudaSuccess) break;
+        }
+        if ((e = cudaEventCreateWithFlags(&s.e_h2d, cudaEventDisableTiming)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.e_kernel, cudaEventDisableTiming)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.e_done, cudaEventDisableTiming)) != cudaSuccess) break;
+    }
+    if (e != cudaSuccess) {
+        ring_free(r);
+        return spx_set_error(SPX_E_NOMEM, "ring allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = r;
+    return SPX_OK;
+}
+
+extern "C" int spx_ring_destroy(spx_ring* r) {
+    if (!r) return SPX_OK;
+    cudaSetDevice(r->plan->cfg.device);
+    cudaStreamSynchronize(r->plan->s_h2d);
+    cudaStreamSynchronize(r->plan->s_compute);
+    cudaStreamSynchronize(r->plan->s_d2h);
+    ring_free(r);
+    return SPX_OK;
+}
+
+extern "C" int spx_ring_acquire(spx_ring* r, void** host_slot, int64_t* capacity_samples) {
+    if (!r || !host_slot) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(r->mu);
+    RingSlot& s = r->slots[(size_t)r->head];
+    if (s.state != 0) return spx_set_error(SPX_E_BUSY, "ring full: collect/release the oldest slot first");
+    s.state = 1;
+    *host_slot = s.h_in;
+    if (capacity_samples) *capacity_samples = r->cfg.slot_samples;
+    return SPX_OK;
+}
+
+extern "C" int spx_ring_commit(spx_ring* r, int64_t n_samples) {
+    if (!r) return spx_set_error(SPX_E_INVALID, "ring is NULL");
+    std::lock_guard<std::mutex> g(r->mu);
+    RingSlot& s = r->slots[(size_t)r->head];
+    if (s.state != 1) return spx_set_error(SPX_E_INVALID, "commit without acquire");
+    if (n_samples < 0 || n_samples > r->cfg.slot_samples) return spx_set_error(SPX_E_INVALID, "n_samples out of range");
+    spx_plan* pl = r->plan;
+    std::lock_guard<std::mutex> gp(pl->mu);
+    SPX_CUDA(cudaSetDevice(pl->cfg.device));
+    const int N = pl->cfg.nfft, hop = pl->cfg.hop;
+    const size_t elt = r->elt;
+    const long long carry = r->carry;
+    // H2D of the new samples behind the carried tail
+    if (n_samples) SPX_CUDA(cudaMemcpyAsync(s.d_in + (size_t)carry * elt, s.h_in, (size_t)n_samples * elt, cudaMemcpyHostToDevice, pl->s_h2d));
+    SPX_CUDA(cudaEventRecord(s.e_h2d, pl->s_h2d));
+    SPX_CUDA(cudaStreamWaitEvent(pl->s_compute, s.e_h2d, 0));
+    const long long avail = carry + n_samples;
+    const long long F = spx_frame_count(avail, N, hop);
+    if (s.d_welch) SPX_CUDA(cudaMemsetAsync(s.d_welch, 0, (size_t)N * sizeof(double), pl->s_compute));
+    if (s.d_max) SPX_CUDA(cudaMemsetAsync(s.d_max, 0, (size_t)N * sizeof(float), pl->s_compute));
+    SPX_TRY(stft_launch_device(pl, s.d_in, 1, 0, F, s.d_db, s.d_wf, nullptr, s.d_welch, s.d_max, r->cfg.vmin, r->cfg.vmax, pl->s_compute));
+    // carry the unconsumed tail into the head of the next slot's device buffer
+    const long long consumed = F * hop;
+    const long long new_carry = avail - consumed;
+    RingSlot& nx = r->slots[(size_t)((r->head + 1) % r->cfg.n_slots)];
+    if (new_carry > 0)
+        SPX_CUDA(cudaMemcpyAsync(nx.d_in, s.d_in + (size_t)consumed * elt, (size_t)new_carry * elt, cudaMemcpyDeviceToDevice, pl->s_compute));
+    SPX_CUDA(cudaEventRecord(s.e_kernel, pl->s_compute));
+    // drain the slot's results
+    SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, s.e_kernel, 0));
+    long long d2h = 0;
+    if (s.d_wf && F) { SPX_CUDA(cudaMemcpyAsync(s.h_wf, s.d_wf, (size_t)F * N, cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += F * N; }
+    if (s.d_db && F) { SPX_CUDA(cudaMemcpyAsync(s.h_db, s.d_db, (size_t)F * N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += F * N * 4; }
+    if (s.d_welch) { SPX_CUDA(cudaMemcpyAsync(s.h_welch, s.d_welch, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += N * 8; }
+    if (s.d_max) { SPX_CUDA(cudaMemcpyAsync(s.h_max, s.d_max, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += N * 4; }
+    SPX_CUDA(cudaEventRecord(s.e_done, pl->s_d2h));
+    s.seq = r->seq++;
+    s.n_frames = F;
+    s.first_frame = r->frames_total;
+    s.h2d_bytes = n_samples * (long long)elt;
+    s.d2h_bytes = d2h;
+    s.state = 2;
+    r->carry = new_carry;
+    r->frames_total += F;
+    r->samples_total += n_samples;
+    r->h2d_total += s.h2d_bytes;
+    r->d2h_total += d2h;
+    r->head = (r->head + 1) % r->cfg.n_slots;
+    r->in_flight++;
+    return SPX_OK;
+}
+
+extern "C" int spx_ring_collect(spx_ring* r, spx_ring_result* out) {
+    if (!r || !out) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    RingSlot* s;
+    {
+        std::lock_guard<std::mutex> g(r->mu);
+        if (r->in_flight == 0) return spx_set_error(SPX_E_BUSY, "nothing committed");
+        s = &r->slots[(size_t)r->tail];
+    }
+    SPX_CUDA(cudaEventSynchronize(s->e_done));   // outside the lock: the producer may keep committing
+    memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(*out);
+    out->seq = s->seq;
+    out->n_frames = s->n_frames;
+    out->first_frame = s->first_frame;
+    out->wf_rows = s->h_wf;
+    out->db_rows = s->h_db;
+    out->welch_acc = s->h_welch;
+    out->maxhold = s->h_max;
+    out->h2d_bytes = s->h2d_bytes;
+    out->d2h_bytes = s->d2h_bytes;
+    return SPX_OK;
+}
+
+extern "C" int spx_ring_release(spx_ring* r) {
+    if (!r) return spx_set_error(SPX_E_INVALID, "ring is NULL");
+    std::lock_guard<std::mutex> g(r->mu);
+    if (r->in_flight == 0) return spx_set_error(SPX_E_BUSY, "nothing to release");
+    RingSlot& s = r->slots[(size_t)r->tail];
+    SPX_CUDA(cudaEventSynchronize(s.e_done));
+    s.state = 0;
+    r->tail = (r->tail + 1) % r->cfg.n_slots;
+    r->in_flight--;
+    return SPX_OK;
+}
+
+extern "C" int spx_ring_stats(spx_ring* r, spx_ring_stats_t* out) {
+    if (!r || !out) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(r->mu);
+    out->struct_size = sizeof(*out);
+    out->h2d_bytes = r->h2d_total;
+    out->d2h_bytes = r->d2h_total;
+    out->samples = r->samples_total;
+    out->frames = r->frames_total;
+    out->in_flight = r->in_flight;
+    out->reserved = 0;
+    return SPX_OK;
+}

@@ -245,8 +245,9 @@ def test_large_n_four_step_parity(sp, nfft, hop, kind, fmt):
     assert r.n_frames == F
     X = oracle_rows(x, nfft, hop, kind, fmt=fmt)
     P = X.real**2 + X.imag**2
-    # fp32 FFT error: a floor relative to the frame's RMS bin level plus a part relative to the bin itself
-    assert np.all(np.abs(r.spectrum - X) <= 6e-6 * np.sqrt(P.mean()) + 1e-6 * np.abs(X))
+    # fp32 FFT error: a floor relative to the frame's RMS bin level, a part relative to the bin itself, and
+    # correlated-rounding spurs of the dominant tone (measured: -149 dBc at k0 + N/2 for N = 2^18)
+    assert np.all(np.abs(r.spectrum - X) <= 6e-6 * np.sqrt(P.mean()) + 1e-6 * np.abs(X) + 1e-7 * np.abs(X).max())
     parity.check_db_rows(r.db_rows, P, what=f"N={nfft}")
     parity.check_power(r.welch_acc[0], P.sum(axis=0), what="welch")
     parity.check_power(r.maxhold[0], P.max(axis=0), what="maxhold")
