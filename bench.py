@@ -51,50 +51,72 @@ def measured_peaks():
 
 def synth_ci16(n, seed):
     """QPSK + CW tone + AWGN, 12-bit range int16; a 4 Mi-sample block tiled to n."""
-    from oracle import spectral_ref as sref
-    base = sref.to_ci16(sref.synth_iq(1 << 22, seed=seed, tone_cycles_per_sample=1500.37 / 4096))
-    reps = -(-n // (1 << 22))
-    return np.tile(base.reshape(-1, 2), (reps, 1))[:n].reshape(-1)
+    from sdr_iq_visualizer_b200 import synth
+    return synth.tiled_ci16(n, seed)
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line):
+    NVML in a thread every 5 ms; nvidia-smi --query-gpu as the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
-        self.rows = []
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.idx])
+                except Exception:
+                    phys = self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = (pynvml, h)
         except Exception:
-            self.proc = None
+            self._nvml = None
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+        self.sm.append(float(out[0])); self.max_mhz = float(out[1])
+        for bit, v in zip((0x8, 0x40, 0x20, 0x4), out[2:6]):
+            if v.strip().lower().startswith("active"):
+                self.mask |= bit
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                if self._nvml:
+                    nv, h = self._nvml
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                else:
+                    self._sample_smi()
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=15)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def dist_setup(n_gpus):
@@ -190,34 +212,41 @@ def main():
     pl = sp.SpectralPlan(NFFT, HOP, "hann", sp.FMT_CI16, device=dev, variant=variant)
     F = pl.frame_count(L_STEP)
 
-    # ---------------- device-resident leg
+    # ---------------- device-resident leg: every launch of a step goes to the plan's compute stream
     d_in = nat.DeviceArray.from_host(host_in, dev)
     d_wf = nat.DeviceArray((F, NFFT), np.uint8, dev)
     d_we = nat.DeviceArray((1, NFFT), np.float64, dev)
     d_mh = nat.DeviceArray((1, NFFT), np.float32, dev)
-    kernel_ms = []
+    d_pxx = nat.DeviceArray((NFFT,), np.float64, dev)
+    d_pdb = nat.DeviceArray((NFFT,), np.float64, dev)
+    st = pl.stream
+    total_timer = nat.DeviceTimer(dev, st)
+    kernel_timers = [nat.DeviceTimer(dev, st) for _ in range(args.steps)]
 
-    def device_step(timed):
-        # one fused STFT launch bracketed by CUDA events on its stream, then PSD finalize + features
-        res, ms = pl.time_stft(d_in, warmup=0, iters=1, wf_rows=d_wf, welch=d_we, maxhold=d_mh, vmin=VMIN, vmax=VMAX)
-        if timed:
-            kernel_ms.extend(ms)
-        _, pdb = pl.welch_finalize(d_we, res.n_frames, FS)
-        return features.measure_batch(pdb, n=NFFT, batch=1, device=dev)[0]
+    def device_step(ktimer):
+        # fused STFT launch (bracketed by its own CUDA events when timed), Welch finalize, classifier features
+        if ktimer is not None:
+            ktimer.start()
+        res = pl.stft(d_in, wf_rows=d_wf, welch=d_we, maxhold=d_mh, vmin=VMIN, vmax=VMAX)
+        if ktimer is not None:
+            ktimer.stop()
+        pl.welch_finalize(d_we, res.n_frames, FS, pxx=d_pxx, pdb=d_pdb)
+        return features.measure_batch(d_pdb, n=NFFT, batch=1, device=dev, stream=st)[0]
 
     for _ in range(args.warmup):
-        feat = device_step(False)
+        feat = device_step(None)
     sampler = ClockSampler(dev)
     if dist is not None:
         dist.barrier()
     nat.device_sync(dev)
     sampler.start()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        feat = device_step(True)
+    total_timer.start()
+    for i in range(args.steps):
+        feat = device_step(kernel_timers[i])
+    total_timer.stop()
+    dt_dev = total_timer.elapsed_ms() * 1e-3
     nat.device_sync(dev)
-    dt_dev = time.perf_counter() - t0
-    clocks = sampler.stop()
+    kernel_ms = [t.elapsed_ms() for t in kernel_timers]
     dt_dev = barrier_max(dist, local, dt_dev)
 
     # ---------------- end-to-end leg: host (pinned) buffers through the C ABI, copies inside the timed region
@@ -240,7 +269,9 @@ def main():
     for _ in range(e2e_steps):
         r, feat_h = e2e_step()
     nat.device_sync(dev)
-    dt_e2e = barrier_max(dist, local, time.perf_counter() - t0)
+    dt_e2e_local = time.perf_counter() - t0
+    clocks = sampler.stop()     # sampled through both timed regions (device-resident leg and end-to-end leg)
+    dt_e2e = barrier_max(dist, local, dt_e2e_local)
     h2d = r.h2d_bytes + NFFT * 8
     d2h = r.d2h_bytes + NFFT * 8 + 160
 
@@ -265,6 +296,8 @@ def main():
                                "75% overlap -> u8 waterfall rows + Welch + max-hold + classifier features",
                    "nfft": NFFT, "hop": HOP, "frames_per_step": F, "kernel_variant": variant,
                    "l2": "step input (246 MB) + rows (246 MB) exceed the 126 MB L2; no explicit flush",
+                   "timing": "CUDA events on the plan's compute stream around the K steps (max over ranks); "
+                             "the STFT kernel additionally bracketed per launch",
                    "multi_gpu": "replicas only: one independent stream per GPU, no data-path collective",
                    "real_time_margin_x": round(L_STEP * args.steps / dt_dev / FS, 1)},
         "e2e": {"value": round(world * L_STEP * e2e_steps / dt_e2e / 1e6, 1), "unit": "Msamples/s",

@@ -147,6 +147,19 @@ SPX_API int spx_stft_time(spx_plan* plan, spx_stft_args* args, int32_t warmup, i
 SPX_API int spx_welch_finalize(spx_plan* plan, int32_t mem, const double* welch_acc, int64_t n_frames, double fs,
                        double* pxx, double* pxx_db, void* stream);
 
+/* The plan's compute stream (cudaStream_t), so that callers can order their own SPX_MEM_DEVICE calls
+ * (spx_welch_finalize, spx_classify_features, spx_timer_*) after the plan's kernels. */
+SPX_API int spx_plan_stream(spx_plan* plan, void** stream_out);
+
+/* Device-side stopwatch: a pair of CUDA events recorded on `stream` (NULL = the legacy default stream).
+ * spx_timer_elapsed_ms waits for the stop event.  Used by bench.py to time K steps on the launching stream. */
+typedef struct spx_timer spx_timer;
+SPX_API int spx_timer_create(int32_t device, spx_timer** out);
+SPX_API int spx_timer_start(spx_timer* t, void* stream);
+SPX_API int spx_timer_stop(spx_timer* t, void* stream);
+SPX_API int spx_timer_elapsed_ms(spx_timer* t, float* ms_out);
+SPX_API int spx_timer_destroy(spx_timer* t);
+
 /* sum(w^2) and sum(w) of the plan's float64 window (in_scale is applied to the data, not counted here) */
 SPX_API int spx_plan_window_sums(spx_plan* plan, double* sum_w2, double* sum_w);
 

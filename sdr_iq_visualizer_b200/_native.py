@@ -126,6 +126,12 @@ _SIGNATURES = {
     "spx_ring_release": (C.c_int, [C.c_void_p]),
     "spx_ring_stats": (C.c_int, [C.c_void_p, C.POINTER(spx_ring_stats_t)]),
     "spx_plan_window_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "spx_plan_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "spx_timer_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "spx_timer_start": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "spx_timer_stop": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "spx_timer_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "spx_timer_destroy": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None
@@ -283,6 +289,37 @@ class DeviceArray:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class DeviceTimer:
+    """A pair of CUDA events recorded on a stream (spx_timer_*): device time of what ran in between."""
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self._h = C.c_void_p()
+        self.stream = stream or None
+        check(lib().spx_timer_create(device, C.byref(self._h)))
+
+    def start(self) -> None:
+        check(lib().spx_timer_start(self._h, self.stream))
+
+    def stop(self) -> None:
+        check(lib().spx_timer_stop(self._h, self.stream))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().spx_timer_elapsed_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib().spx_timer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

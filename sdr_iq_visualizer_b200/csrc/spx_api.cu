@@ -405,6 +405,61 @@ int spx_plan_sync(spx_plan* pl) {
     return SPX_OK;
 }
 
+int spx_plan_stream(spx_plan* pl, void** stream_out) {
+    if (!pl || !stream_out) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    *stream_out = (void*)pl->s_compute;
+    return SPX_OK;
+}
+
+struct spx_timer {
+    int device;
+    cudaEvent_t e0, e1;
+};
+
+int spx_timer_create(int32_t device, spx_timer** out) {
+    if (!out) return spx_set_error(SPX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    SPX_CUDA(cudaSetDevice(device));
+    spx_timer* t = new (std::nothrow) spx_timer();
+    if (!t) return spx_set_error(SPX_E_NOMEM, "out of host memory");
+    t->device = device;
+    cudaError_t e = cudaEventCreate(&t->e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&t->e1);
+    if (e != cudaSuccess) {
+        delete t;
+        return spx_set_error(SPX_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return SPX_OK;
+}
+int spx_timer_start(spx_timer* t, void* stream) {
+    if (!t) return spx_set_error(SPX_E_INVALID, "timer is NULL");
+    SPX_CUDA(cudaSetDevice(t->device));
+    SPX_CUDA(cudaEventRecord(t->e0, (cudaStream_t)stream));
+    return SPX_OK;
+}
+int spx_timer_stop(spx_timer* t, void* stream) {
+    if (!t) return spx_set_error(SPX_E_INVALID, "timer is NULL");
+    SPX_CUDA(cudaSetDevice(t->device));
+    SPX_CUDA(cudaEventRecord(t->e1, (cudaStream_t)stream));
+    return SPX_OK;
+}
+int spx_timer_elapsed_ms(spx_timer* t, float* ms_out) {
+    if (!t || !ms_out) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    SPX_CUDA(cudaSetDevice(t->device));
+    SPX_CUDA(cudaEventSynchronize(t->e1));
+    SPX_CUDA(cudaEventElapsedTime(ms_out, t->e0, t->e1));
+    return SPX_OK;
+}
+int spx_timer_destroy(spx_timer* t) {
+    if (!t) return SPX_OK;
+    cudaSetDevice(t->device);
+    cudaEventDestroy(t->e0);
+    cudaEventDestroy(t->e1);
+    delete t;
+    return SPX_OK;
+}
+
 int spx_plan_window_sums(spx_plan* pl, double* sum_w2, double* sum_w) {
     if (!pl) return spx_set_error(SPX_E_INVALID, "plan is NULL");
     if (sum_w2) *sum_w2 = pl->sum_w2;  // window only: in_scale belongs to the data

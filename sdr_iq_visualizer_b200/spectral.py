@@ -199,16 +199,24 @@ class SpectralPlan:
         res = self.stft(x, _time=(int(warmup), int(iters), bool(flush_l2)), **kw)
         return res, self.last_times_ms
 
-    def welch_finalize(self, welch_acc, n_frames: int, sample_rate: float, want_db: bool = True):
-        """mlab.psd density and its dB from an accumulated numerator (one stream)."""
+    @property
+    def stream(self) -> int:
+        """cudaStream_t (as int) of the plan's compute stream, for ordering device-memory calls after its kernels."""
+        st = C.c_void_p()
+        nat.check(nat.lib().spx_plan_stream(self._h, C.byref(st)))
+        return int(st.value or 0)
+
+    def welch_finalize(self, welch_acc, n_frames: int, sample_rate: float, want_db: bool = True, pxx=None, pdb=None):
+        """mlab.psd density and its dB from an accumulated numerator (one stream).  ``pxx`` / ``pdb`` may be
+        caller buffers (same memory space as ``welch_acc``) to avoid an allocation per call."""
         p, mem = nat.as_ptr(welch_acc)
         N = self.nfft
         if mem == MEM_HOST:
-            pxx = np.empty(N, np.float64)
-            pdb = np.empty(N, np.float64) if want_db else None
+            pxx = np.empty(N, np.float64) if pxx is None else pxx
+            pdb = (np.empty(N, np.float64) if want_db else None) if pdb is None else pdb
         else:
-            pxx = DeviceArray((N,), np.float64, self.device)
-            pdb = DeviceArray((N,), np.float64, self.device) if want_db else None
+            pxx = DeviceArray((N,), np.float64, self.device) if pxx is None else pxx
+            pdb = (DeviceArray((N,), np.float64, self.device) if want_db else None) if pdb is None else pdb
         nat.check(nat.lib().spx_welch_finalize(self._h, mem, p, int(n_frames), float(sample_rate), nat.as_ptr(pxx)[0],
                                                nat.as_ptr(pdb)[0], None))
         return pxx, pdb
