@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A) big_cols_kernel(con
         for (int t = 0; t < 16; ++t) {
             const int i = N2 * (tid + t * T1) + n2;
             if (FMT == FMT_CF32) v[t] = ld_stream_cf32(reinterpret_cast<const float2*>(p.in) + s0 + i);
-            else                 v[t] = ld_stream_ci16(reinterpret_cast<const short2*>(p.in) + s0 + i);
+            else                 v[t] = ld_stream_ci16<TUNE_I2FP>(reinterpret_cast<const short2*>(p.in) + s0 + i);
         }
         if (p.win != nullptr) {
 #pragma unroll

@@ -4,7 +4,7 @@
 namespace spx {
 int launch_stft_4k(StftLaunch& L) {
     switch (L.variant) {
-        case 0: return launch_stft_n<4096, TW_REG, 2, true>(L);   // default: TMA-staged input, register twiddle bases
+        case 0: return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);  // default: TMA-staged input, register twiddle bases, int16 -> float on the ALU pipe
         case 8: return launch_stft_n<4096, TW_LDG, 2>(L);
         case 1: return launch_stft_n<4096, TW_LDG, 3>(L);
         case 2: return launch_stft_n<4096, TW_REG, 2>(L);
@@ -13,6 +13,8 @@ int launch_stft_4k(StftLaunch& L) {
         case 5: return launch_stft_n<4096, TW_REG, 2, true>(L);   // same as 0
         case 6: return launch_stft_n<4096, TW_LDG, 2, true>(L);
         case 7: return launch_stft_n<4096, TW_HYB, 2, true>(L);   // pass-1 twiddles from smem, pass-2 from registers
+        case 10: return launch_stft_n<4096, TW_HYB, 2, true, TUNE_I2FP>(L);
+        case 9: return launch_stft_n<4096, TW_REG, 2, true>(L);   // int16 -> float with I2F.S16 (XU pipe)
         default: return spx_set_error(SPX_E_INVALID, "unknown kernel variant %d for nfft 4096", L.variant);
     }
 }

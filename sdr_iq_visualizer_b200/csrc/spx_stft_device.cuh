@@ -31,6 +31,7 @@ struct StftParams {
     float db_eps;                // 20*log10(|X| + db_eps)
     float db_pw_min;             // below this |X|^2 the eps term matters and the exact form is evaluated
     float q_vmin, q_scale;       // u8 = sat(floor((db - vmin) * scale)), scale = 256/(vmax-vmin)
+    float q_a, q_b;              // the same map on log2|X|^2:  (db - vmin) * scale = q_a * log2|X|^2 + q_b
     int frames_per_chunk;        // accumulator flush granularity (<= 256)
     int chunks_per_stream;
     long long total_chunks;
@@ -46,12 +47,27 @@ SPX_HD float2 ld_stream_cf32(const float2* p) {
     return *p;
 #endif
 }
+enum { TUNE_I2FP = 1 };  // kernel tuning bits (template parameter TUNE)
+
+// packed int16 I,Q -> float2.  Default: two I2F.S16 (XU pipe, 16 lanes/clk/SM).  TUNE_I2FP: sign-extend with
+// PRMT and convert with I2FP.F32.S32 (ALU pipe) -- exact either way (|v| <= 2^15 fits a float).
+template <int TUNE>
+SPX_HD float2 ci16_to_f2(unsigned int w) {
+#ifdef __CUDA_ARCH__
+    if constexpr ((TUNE & TUNE_I2FP) != 0) {
+        const int lo = (int)__byte_perm(w, 0u, 0x9910), hi = (int)__byte_perm(w, 0u, 0xbb32);
+        return make_float2((float)lo, (float)hi);
+    }
+#endif
+    const short lo = (short)(w & 0xffffu), hi = (short)(w >> 16);
+    return make_float2((float)lo, (float)hi);
+}
+template <int TUNE = 0>
 SPX_HD float2 ld_stream_ci16(const short2* p) {
 #ifdef __CUDA_ARCH__
     unsigned int w;
     asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(w) : "l"(p));
-    short lo = (short)(w & 0xffffu), hi = (short)(w >> 16);
-    return make_float2((float)lo, (float)hi);
+    return ci16_to_f2<TUNE>(w);
 #else
     return make_float2((float)p->x, (float)p->y);
 #endif
@@ -101,6 +117,15 @@ SPX_HD unsigned int sat_floor_u8(float q) {
 SPX_HD float amp_db_fast(float pw) { return (0.5f * SPX_DB_PER_LOG2) * fast_log2(pw); }
 SPX_HD float amp_db_exact(float pw, float eps) { return SPX_DB_PER_LOG2 * fast_log2(fast_sqrt(pw) + eps); }
 
+// pre-floor colormap value from y = log2|X|^2 in one FMA: (dB - vmin) * scale = q_a * y + q_b
+SPX_HD float quant_pre(float y, float q_a, float q_b) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(y, q_a, q_b);
+#else
+    return fmaf(y, q_a, q_b);
+#endif
+}
+
 // ------------------------------------------------------------------ per-thread state
 template <bool ACC>
 struct StftAcc {
@@ -136,14 +161,14 @@ SPX_HD void tw_regs_load_pass(TwRegs<N>& r, int tid, const float2* tw) {
 }
 
 // ------------------------------------------------------------------ pass pieces
-template <int N, int FMT>
+template <int N, int FMT, int TUNE = 0>
 SPX_HD void load_frame(float2* v, const StftParams& p, long long sample0, int tid) {
     constexpr int T = N / 16;
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
         const long long i = sample0 + tid + t * T;
         if (FMT == FMT_CF32) v[t] = ld_stream_cf32(reinterpret_cast<const float2*>(p.in) + i);
-        else                 v[t] = ld_stream_ci16(reinterpret_cast<const short2*>(p.in) + i);
+        else                 v[t] = ld_stream_ci16<TUNE>(reinterpret_cast<const short2*>(p.in) + i);
     }
     if (p.win != nullptr) {
 #pragma unroll
@@ -158,7 +183,7 @@ SPX_HD void load_frame(float2* v, const StftParams& p, long long sample0, int ti
 // pass 0 input from the shared-memory staging buffer that a bulk async copy (TMA) filled
 // `win_half` is the first N/2 entries of the (symmetric) window in shared memory:
 // w[i] = win_half[i] for i < N/2, win_half[N-1-i] otherwise (np.hanning / np.blackman are exactly symmetric)
-template <int N, int FMT>
+template <int N, int FMT, int TUNE = 0>
 SPX_HD void load_frame_staged(float2* v, const void* stage, const float* win_half, int tid) {
     constexpr int T = N / 16;
 #pragma unroll
@@ -166,8 +191,7 @@ SPX_HD void load_frame_staged(float2* v, const void* stage, const float* win_hal
         if (FMT == FMT_CF32) {
             v[t] = reinterpret_cast<const float2*>(stage)[tid + t * T];
         } else {
-            const short2 s = reinterpret_cast<const short2*>(stage)[tid + t * T];
-            v[t] = make_float2((float)s.x, (float)s.y);
+            v[t] = ci16_to_f2<TUNE>(reinterpret_cast<const unsigned int*>(stage)[tid + t * T]);
         }
     }
     if (win_half != nullptr) {
@@ -286,19 +310,20 @@ SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, Stf
         float m67 = fminf(v[6].x, v[7].x), m89 = fminf(v[8].x, v[9].x), mab = fminf(v[10].x, v[11].x);
         float mcd = fminf(v[12].x, v[13].x), mef = fminf(v[14].x, v[15].x);
         const float pmin = fminf(fminf(fminf(m01, m23), fminf(m45, m67)), fminf(fminf(m89, mab), fminf(mcd, mef)));
+        // v[i].y = log2 of the (eps-corrected) power: dB = (10 log10 2) * y
         if (pmin >= p.db_pw_min) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i].y = amp_db_fast(v[i].x);
+            for (int i = 0; i < 16; ++i) v[i].y = fast_log2(v[i].x);
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i].y = amp_db_exact(v[i].x, p.db_eps);
+            for (int i = 0; i < 16; ++i) v[i].y = 2.0f * fast_log2(fast_sqrt(v[i].x) + p.db_eps);
         }
         if (p.db_rows) {
             float* db = p.db_rows + row * N + tid;
 #pragma unroll
             for (int u = 0; u < NB; ++u)
 #pragma unroll
-                for (int t = 0; t < R; ++t) db[shift_off<N>(t) + T * u] = v[u * R + t].y;
+                for (int t = 0; t < R; ++t) db[shift_off<N>(t) + T * u] = (0.5f * SPX_DB_PER_LOG2) * v[u * R + t].y;
         }
         if (p.wf_rows) {
             unsigned char* wf = p.wf_rows + row * N + tid;
@@ -306,7 +331,7 @@ SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, Stf
             for (int u = 0; u < NB; ++u)
 #pragma unroll
                 for (int t = 0; t < R; ++t)
-                    wf[shift_off<N>(t) + T * u] = (unsigned char)sat_floor_u8((v[u * R + t].y - p.q_vmin) * p.q_scale);
+                    wf[shift_off<N>(t) + T * u] = (unsigned char)sat_floor_u8(quant_pre(v[u * R + t].y, p.q_a, p.q_b));
         }
     }
 }
@@ -320,15 +345,15 @@ SPX_HD int acc_pos(int tid, int idx) {
 
 // ------------------------------------------------------------------ one frame, phase by phase
 // phase k (0 <= k < P) = pass k; barriers between phases are the caller's job.
-template <int N, int FMT, bool ACC, int TWM, int S>
+template <int N, int FMT, bool ACC, int TWM, int S, int TUNE = 0>
 SPX_HD void stft_phase(float2* v, int tid, const StftParams& p, long long sample0, long long row, bool active,
                        float2* bufA, float2* bufB, const float2* tw, const TwRegs<N>& twr, StftAcc<ACC>& acc,
                        const void* stage = nullptr, const float* win_half = nullptr) {
     constexpr int P = plan_passes(N);
     if (!active) return;
     if constexpr (S == 0) {
-        if (stage) load_frame_staged<N, FMT>(v, stage, win_half, tid);
-        else load_frame<N, FMT>(v, p, sample0, tid);
+        if (stage) load_frame_staged<N, FMT, TUNE>(v, stage, win_half, tid);
+        else load_frame<N, FMT, TUNE>(v, p, sample0, tid);
     } else {
         const float2* src = ((S - 1) & 1) ? bufB : bufA;
         pass_load_smem<N, S>(v, tid, src);

@@ -93,7 +93,7 @@ struct FrameCursor {
     __device__ __forceinline__ long long row() const { return rbase + fi; }
 };
 
-template <int N, int FMT, bool ACC, int TWM, int OCC, bool STAGE>
+template <int N, int FMT, bool ACC, int TWM, int OCC, bool STAGE, int TUNE = 0>
 __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const StftParams p) {
     using C = StftCfg<N>;
     constexpr int P = C::P;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const St
             mbar_wait(bar_u32, parity);
             parity ^= 1u;
         }
-        stft_phase<N, FMT, ACC, TWM, 0>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc, stage, win_half);
+        stft_phase<N, FMT, ACC, TWM, 0, TUNE>(v, tid, p, s0, row, true, bufA, bufB, tw, twr, acc, stage, win_half);
         if constexpr (P > 1 || STAGE) slot_barrier<N>(slot);
         if constexpr (STAGE) {
             // every thread of the slot has read its staged samples: refill the buffer with the next frame
@@ -218,10 +218,10 @@ struct StftLaunch {
     cudaStream_t stream;
 };
 
-template <int N, int FMT, bool ACC, int TWM, int OCC, bool STAGE>
+template <int N, int FMT, bool ACC, int TWM, int OCC, bool STAGE, int TUNE = 0>
 int launch_stft_inst(StftLaunch& L) {
     using C = StftCfg<N>;
-    auto kern = stft_kernel<N, FMT, ACC, TWM, OCC, STAGE>;
+    auto kern = stft_kernel<N, FMT, ACC, TWM, OCC, STAGE, TUNE>;
     size_t smem = (size_t)(C::FPC * C::slot_f2(STAGE, FMT) + C::win_f2(STAGE)) * sizeof(float2);
     if (TWM == TW_SMEM) smem += (size_t)C::TW_F2 * sizeof(float2);
     if (TWM == TW_HYB) smem += (size_t)plan_tw_offset(N, 2) * sizeof(float2);
@@ -267,24 +267,24 @@ inline bool stage_ok(const StftLaunch& L) {
     return true;
 }
 
-template <int N, int TWM, int OCC, bool STAGE>
+template <int N, int TWM, int OCC, bool STAGE, int TUNE = 0>
 int launch_stft_fmt(StftLaunch& L) {
     const bool acc = L.p.welch_acc != nullptr || L.p.maxhold != nullptr;
     if (L.in_fmt == FMT_CF32) {
-        return acc ? launch_stft_inst<N, FMT_CF32, true, TWM, OCC, STAGE>(L)
-                   : launch_stft_inst<N, FMT_CF32, false, TWM, OCC, STAGE>(L);
+        return acc ? launch_stft_inst<N, FMT_CF32, true, TWM, OCC, STAGE, TUNE>(L)
+                   : launch_stft_inst<N, FMT_CF32, false, TWM, OCC, STAGE, TUNE>(L);
     }
-    return acc ? launch_stft_inst<N, FMT_CI16, true, TWM, OCC, STAGE>(L)
-               : launch_stft_inst<N, FMT_CI16, false, TWM, OCC, STAGE>(L);
+    return acc ? launch_stft_inst<N, FMT_CI16, true, TWM, OCC, STAGE, TUNE>(L)
+               : launch_stft_inst<N, FMT_CI16, false, TWM, OCC, STAGE, TUNE>(L);
 }
 
 // STAGE_WANTED: use the TMA-staged kernel when the input is suitably aligned, else direct loads
-template <int N, int TWM, int OCC, bool STAGE_WANTED = false>
+template <int N, int TWM, int OCC, bool STAGE_WANTED = false, int TUNE = 0>
 int launch_stft_n(StftLaunch& L) {
     if constexpr (STAGE_WANTED && StftCfg<N>::CAN_STAGE) {
-        if (stage_ok(L)) return launch_stft_fmt<N, TWM, OCC, true>(L);
+        if (stage_ok(L)) return launch_stft_fmt<N, TWM, OCC, true, TUNE>(L);
     }
-    return launch_stft_fmt<N, TWM, OCC, false>(L);
+    return launch_stft_fmt<N, TWM, OCC, false, TUNE>(L);
 }
 
 // one translation unit per size group instantiates these

@@ -59,6 +59,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--variants", default="0,1,2,3,4")
+    ap.add_argument("--only4k", action="store_true")
     args = ap.parse_args()
     print(json.dumps(nat.device_info(0)))
     L = 1 << 24 if args.quick else 61_440_000
@@ -69,6 +70,8 @@ def main():
         run_case("cf32 hop=N u8", 4096, 4096, "hann", sp.FMT_CF32, L, ["u8"], v)
         run_case("cf32 hop=N acc only", 4096, 4096, "hann", sp.FMT_CF32, L, ["acc"], v)
         run_case("cf32 50% f32", 4096, 2048, "hann", sp.FMT_CF32, L, ["db"], v)
+    if args.only4k:
+        return
     for n in (65536, 16384, 1 << 18):
         run_case(f"cf32 N={n} 50% u8+acc (C5 shape)", n, n // 2, "hann", sp.FMT_CF32, 1 << 26, ["u8", "acc"], 0, iters=5)
         run_case(f"cf32 N={n} hop=N f32", n, n, "hann", sp.FMT_CF32, 1 << 26, ["db"], 0, iters=5)
