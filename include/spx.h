@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SPX_ABI_VERSION 1
+#define SPX_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SPX_API __attribute__((visibility("default")))
@@ -90,6 +90,16 @@ SPX_API int spx_memcpy_d2h(int device, void* dst, const void* src, size_t bytes)
 SPX_API int spx_memset(int device, void* dst, int value, size_t bytes);
 SPX_API int spx_device_sync(int device);
 
+/* ---------------------------------------------------------------- peer memory (one process per GPU)
+ * The multi-GPU configs reduce partial Welch sums / max-holds and collect waterfall rows on one rank
+ * (SURVEY.md section 8(e)).  Instead of a separate collective, the owner exports its buffers and every rank's
+ * STFT kernel writes / reduces straight into them over NVLink (spx_stft_args.peer_outputs).
+ * spx_ipc_export: `dptr` must be the base of an allocation made by spx_device_alloc. */
+#define SPX_IPC_HANDLE_BYTES 64
+SPX_API int spx_ipc_export(int device, void* dptr, void* handle_out);
+SPX_API int spx_ipc_open(int device, const void* handle, void** dptr_out);
+SPX_API int spx_ipc_close(int device, void* dptr);
+
 /* ---------------------------------------------------------------- STFT plan */
 typedef struct spx_plan spx_plan;
 
@@ -130,6 +140,10 @@ typedef struct {
     int64_t n_frames_out; /* out: F */
     int64_t h2d_bytes_out;/* out: bytes copied host->device by this call (SPX_MEM_HOST) */
     int64_t d2h_bytes_out;/* out: bytes copied device->host by this call */
+    int32_t peer_outputs; /* SPX_MEM_DEVICE only: 1 = welch_acc / maxhold / rows may live on ANOTHER GPU (mapped with
+                           * spx_ipc_open); the accumulator flushes then use system-scope atomics so that several GPUs
+                           * can reduce into one buffer over NVLink inside the STFT kernel itself */
+    int32_t reserved;
 } spx_stft_args;
 
 /* windowed STFT -> PSD -> waterfall; replaces streamer.py:119-121 (per buffer) and the frame loop of

@@ -50,7 +50,7 @@ class spx_stft_args(C.Structure):
                 ("db_rows", C.c_void_p), ("wf_rows", C.c_void_p), ("spec_rows", C.c_void_p),
                 ("welch_acc", C.c_void_p), ("maxhold", C.c_void_p), ("vmin", C.c_float), ("vmax", C.c_float),
                 ("stream", C.c_void_p), ("n_frames_out", C.c_int64), ("h2d_bytes_out", C.c_int64),
-                ("d2h_bytes_out", C.c_int64)]
+                ("d2h_bytes_out", C.c_int64), ("peer_outputs", C.c_int32), ("reserved", C.c_int32)]
 
 
 class spx_features(C.Structure):
@@ -127,6 +127,9 @@ _SIGNATURES = {
     "spx_ring_stats": (C.c_int, [C.c_void_p, C.POINTER(spx_ring_stats_t)]),
     "spx_plan_window_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "spx_plan_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "spx_ipc_export": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "spx_ipc_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "spx_ipc_close": (C.c_int, [C.c_int, C.c_void_p]),
     "spx_timer_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "spx_timer_start": (C.c_int, [C.c_void_p, C.c_void_p]),
     "spx_timer_stop": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -293,6 +296,68 @@ class DeviceArray:
             pass
 
 
+class DeviceView:
+    """A typed window into device memory this object does not own: a slice of a DeviceArray, or a peer
+    GPU's buffer mapped with ``PeerBuffer``.  Accepted wherever a DeviceArray is."""
+
+    def __init__(self, ptr: int, shape, dtype, device: int = 0, keep=None):
+        self.ptr = int(ptr)
+        self.shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.device = int(device)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._keep = keep
+
+    def rows(self, r0: int, r1: int) -> "DeviceView":
+        """Rows [r0, r1) of a 2-D view."""
+        pitch = self.shape[1] * self.dtype.itemsize
+        return DeviceView(self.ptr + r0 * pitch, (r1 - r0, self.shape[1]), self.dtype, self.device, self)
+
+
+class PeerBuffer:
+    """One device allocation shared between the ranks of a node (one process per GPU): the owner
+    allocates and exports it (``handle``), the others map it with ``PeerBuffer.open`` and pass
+    ``view()`` as an output of ``SpectralPlan.stft(..., peer_outputs=True)``; their kernels then write
+    and reduce into the owner's HBM over NVLink."""
+
+    def __init__(self, shape, dtype, device: int = 0):
+        self.array = DeviceArray(shape, dtype, device, zero=True)
+        self.shape, self.dtype, self.device = self.array.shape, self.array.dtype, device
+        h = (C.c_ubyte * 64)()
+        check(lib().spx_ipc_export(device, self.array.ptr, h))
+        self.handle = bytes(h)
+        self._mapped = None
+
+    @classmethod
+    def open(cls, handle: bytes, shape, dtype, device: int) -> "PeerBuffer":
+        self = cls.__new__(cls)
+        self.array = None
+        self.shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+        self.dtype, self.device, self.handle = np.dtype(dtype), device, handle
+        p = C.c_void_p()
+        check(lib().spx_ipc_open(device, (C.c_ubyte * 64).from_buffer_copy(handle), C.byref(p)))
+        self._mapped = p.value
+        return self
+
+    def view(self) -> DeviceView:
+        ptr = self.array.ptr if self.array is not None else self._mapped
+        return DeviceView(ptr, self.shape, self.dtype, self.device, self)
+
+    def close(self) -> None:
+        if self._mapped:
+            lib().spx_ipc_close(self.device, self._mapped)
+            self._mapped = None
+        if self.array is not None:
+            self.array.free()
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceTimer:
     """A pair of CUDA events recorded on a stream (spx_timer_*): device time of what ran in between."""
 
@@ -332,7 +397,7 @@ def as_ptr(x) -> tuple:
     """(pointer, mem) of a numpy array, DeviceArray, torch tensor or None."""
     if x is None:
         return None, None
-    if isinstance(x, DeviceArray):
+    if isinstance(x, (DeviceArray, DeviceView)):
         return x.ptr, MEM_DEVICE
     if isinstance(x, np.ndarray):
         if not x.flags.c_contiguous:

@@ -8,6 +8,7 @@
 // rx buffer: /root/reference/app/sdr/streamer.py:123-131,186-194).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -65,7 +66,7 @@ int plan_event(spx_plan* pl, size_t i, cudaEvent_t* out) {
 // ------------------------------------------------------------------ dispatch
 int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long long stream_stride, long long frames,
                        float* db_rows, unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold,
-                       float vmin, float vmax, cudaStream_t st) {
+                       float vmin, float vmax, cudaStream_t st, int sys_atomics) {
     if (frames <= 0 || n_streams <= 0) return SPX_OK;
     if (pl->cfg.nfft >= 16384) {  // four-step path, one stream at a time
         const size_t elt = pl->cfg.in_fmt == SPX_FMT_CI16 ? 4 : 8;
@@ -74,7 +75,7 @@ int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long l
             const size_t r0 = (size_t)(s * frames);
             SPX_TRY(bigfft_launch_stream(pl, (const char*)in + (size_t)(s * stream_stride) * elt, frames, (long long)r0,
                                          db_rows, wf_rows, spec_rows, welch_acc ? welch_acc + s * N : nullptr,
-                                         maxhold ? maxhold + s * N : nullptr, vmin, vmax, st));
+                                         maxhold ? maxhold + s * N : nullptr, vmin, vmax, st, sys_atomics));
         }
         return SPX_OK;
     }
@@ -94,6 +95,7 @@ int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long l
     L.p.maxhold = maxhold;
     L.p.db_eps = pl->cfg.db_eps;
     L.p.db_pw_min = pl->cfg.db_eps * pl->cfg.db_eps * 1099511627776.0f;  // (2^20 eps)^2
+    L.p.sys_atomics = sys_atomics;
     L.p.q_vmin = vmin;
     L.p.q_scale = 256.0f / (vmax - vmin);
     L.p.q_a = (float)(3.01029995663981195214 * 256.0 / ((double)vmax - (double)vmin));  // 10 log10(2) * scale
@@ -223,6 +225,49 @@ static int stft_exec_host(spx_plan* pl, spx_stft_args* a, long long F) {
     return SPX_OK;
 }
 
+// ------------------------------------------------------------------ device execution with peer-resident outputs
+// Multi-GPU capture shards: the accumulators and the waterfall rows live on another GPU.
+// The Welch / max-hold partials are reduced by the STFT kernel itself (system-scope atomics over NVLink, tiny
+// traffic).  The uint8 rows are produced in frame pieces into two local staging buffers and pushed to the peer by
+// the copy engine on `s_d2h` while the next piece is being transformed: full-size NVLink writes instead of the
+// kernel's 16..32-byte row fragments, and the transfer hides behind the transform piece by piece.
+static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cudaStream_t st) {
+    const int N = pl->cfg.nfft, hop = pl->cfg.hop;
+    const size_t elt = in_elt(pl);
+    const long long S = a->n_streams;
+    long long piece = (long long)(pl->peer_piece_bytes / (size_t)N);
+    if (piece < 1) piece = 1;
+    if (piece > F) piece = F;
+    SPX_TRY(pl->st_wf.reserve((size_t)(2 * piece) * N));
+    unsigned char* stage[2] = {(unsigned char*)pl->st_wf.ptr, (unsigned char*)pl->st_wf.ptr + (size_t)piece * N};
+    cudaEvent_t e_k[2], e_c[2];
+    for (int i = 0; i < 2; ++i) {
+        SPX_TRY(plan_event(pl, (size_t)i, &e_k[i]));
+        SPX_TRY(plan_event(pl, (size_t)(2 + i), &e_c[i]));
+    }
+    long long idx = 0;
+    for (long long s = 0; s < S; ++s) {
+        const char* in_s = (const char*)a->in + (size_t)(s * a->stream_stride) * elt;
+        for (long long f_lo = 0; f_lo < F; f_lo += piece, ++idx) {
+            const long long nf = F - f_lo < piece ? F - f_lo : piece;
+            const int b = (int)(idx & 1);
+            if (idx >= 2) SPX_CUDA(cudaStreamWaitEvent(st, e_c[b], 0));   // the copy that last used this buffer is done
+            SPX_TRY(stft_launch_device(pl, in_s + (size_t)(f_lo * hop) * elt, 1, 0, nf, nullptr, stage[b], nullptr,
+                                       a->welch_acc ? a->welch_acc + s * N : nullptr, a->maxhold ? a->maxhold + s * N : nullptr,
+                                       a->vmin, a->vmax, st, 1));
+            SPX_CUDA(cudaEventRecord(e_k[b], st));
+            SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, e_k[b], 0));
+            SPX_CUDA(cudaMemcpyAsync(a->wf_rows + (size_t)(s * F + f_lo) * N, stage[b], (size_t)nf * N, cudaMemcpyDefault, pl->s_d2h));
+            SPX_CUDA(cudaEventRecord(e_c[b], pl->s_d2h));
+        }
+    }
+    // whoever waits on `st` (spx_plan_sync, a later launch) also waits for the last copies
+    SPX_CUDA(cudaStreamWaitEvent(st, e_c[0], 0));
+    if (idx >= 2) SPX_CUDA(cudaStreamWaitEvent(st, e_c[1], 0));
+    a->d2h_bytes_out = 0;
+    return SPX_OK;
+}
+
 __global__ void welch_finalize_kernel(const double* __restrict__ acc, int n, double inv_norm, double* pxx, double* pxx_db) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -326,6 +371,30 @@ int spx_device_sync(int device) {
     return SPX_OK;
 }
 
+int spx_ipc_export(int device, void* dptr, void* handle_out) {
+    if (!dptr || !handle_out) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SPX_IPC_HANDLE_BYTES, "handle size");
+    SPX_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    SPX_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle_out, &h, sizeof(h));
+    return SPX_OK;
+}
+int spx_ipc_open(int device, const void* handle, void** dptr_out) {
+    if (!handle || !dptr_out) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    SPX_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    SPX_CUDA(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SPX_OK;
+}
+int spx_ipc_close(int device, void* dptr) {
+    if (!dptr) return SPX_OK;
+    SPX_CUDA(cudaSetDevice(device));
+    SPX_CUDA(cudaIpcCloseMemHandle(dptr));
+    return SPX_OK;
+}
+
 int spx_plan_create(spx_plan** out, const spx_plan_config* cfg) {
     if (!out || !cfg) return spx_set_error(SPX_E_INVALID, "NULL argument");
     *out = nullptr;
@@ -346,6 +415,9 @@ int spx_plan_create(spx_plan** out, const spx_plan_config* cfg) {
     if (!pl) return spx_set_error(SPX_E_NOMEM, "out of host memory");
     pl->cfg = *cfg;
     if (!(pl->cfg.in_scale != 0.0f)) pl->cfg.in_scale = 1.0f;
+    if (const char* e = getenv("SPX_PEER_PIECE_BYTES")) { long long v = atoll(e); if (v >= 4096) pl->peer_piece_bytes = (size_t)v; }
+    if (const char* e = getenv("SPX_H2D_PIECE_BYTES")) { long long v = atoll(e); if (v >= 65536) pl->piece_bytes = (size_t)v; }
+    if (const char* e = getenv("SPX_BIG_SCRATCH_BYTES")) { long long v = atoll(e); if (v >= (1 << 20)) pl->big_scratch_bytes = (size_t)v; }
     int rc = SPX_OK;
     do {
         cudaError_t e;
@@ -494,8 +566,10 @@ int spx_stft_exec(spx_plan* pl, spx_stft_args* a) {
             if (a->welch_acc) SPX_CUDA(cudaMemsetAsync(a->welch_acc, 0, (size_t)S * N * sizeof(double), st));
             if (a->maxhold) SPX_CUDA(cudaMemsetAsync(a->maxhold, 0, (size_t)S * N * sizeof(float), st));
         }
+        if (a->peer_outputs && a->wf_rows && !a->db_rows && !a->spec_rows && F > 0) return stft_exec_device_peer(pl, a, F, st);
         return stft_launch_device(pl, a->in, S, a->stream_stride, F, a->db_rows, a->wf_rows,
-                                  reinterpret_cast<float2*>(a->spec_rows), a->welch_acc, a->maxhold, a->vmin, a->vmax, st);
+                                  reinterpret_cast<float2*>(a->spec_rows), a->welch_acc, a->maxhold, a->vmin, a->vmax, st,
+                                  a->peer_outputs ? 1 : 0);
     }
     if (F == 0) {
         if (!a->accumulate) {

@@ -45,6 +45,7 @@ struct BigParams {
     float* maxhold;
     float db_eps, db_pw_min, q_vmin, q_scale;
     int frames_per_chunk;    // kernel B: accumulator flush granularity
+    int sys_atomics;         // accumulators may live on a peer GPU
 };
 
 template <int N1, int N2>
@@ -231,8 +232,7 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(con
                 for (int t = 0; t < RL; ++t) {
                     const int k2s = (tid + T2 * u + t * (N2 / RL) + N2 / 2) & (N2 - 1);
                     const long long o = k1 + (long long)N1 * k2s;
-                    if (p.welch_acc) atomicAdd(p.welch_acc + o, (double)acc.sum[u * RL + t]);
-                    if (p.maxhold) atomicMax(reinterpret_cast<unsigned int*>(p.maxhold) + o, __float_as_uint(acc.mx[u * RL + t]));
+                    flush_acc(p.welch_acc, p.maxhold, o, acc.sum[u * RL + t], acc.mx[u * RL + t], p.sys_atomics);
                 }
             acc.reset();
         }
@@ -326,7 +326,7 @@ static int big_launch_pair(spx_plan* pl, BigParams& p, cudaStream_t st) {
 // one stream, frames [0, frames): batches of frames through the L2-sized scratch
 int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
                          unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
-                         float vmax, cudaStream_t st) {
+                         float vmax, cudaStream_t st, int sys_atomics) {
     const int n = pl->cfg.nfft;
     const size_t frame_bytes = (size_t)n * sizeof(float2);
     long long fb = (long long)(pl->big_scratch_bytes / frame_bytes);
@@ -352,6 +352,7 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
     p.db_pw_min = pl->cfg.db_eps * pl->cfg.db_eps * 1099511627776.0f;
     p.q_vmin = vmin;
     p.q_scale = 256.0f / (vmax - vmin);
+    p.sys_atomics = sys_atomics;
     for (long long f0 = 0; f0 < frames; f0 += fb) {
         p.frames = (int)(frames - f0 < fb ? frames - f0 : fb);
         p.sample0 = f0 * pl->cfg.hop;

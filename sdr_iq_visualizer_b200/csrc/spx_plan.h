@@ -28,6 +28,7 @@ struct spx_plan {
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> events;
     size_t piece_bytes = 16u << 20;  // H2D piece size of the host pipeline
+    size_t peer_piece_bytes = 48u << 20;  // uint8 rows per piece of the peer-output pipeline (two staging buffers)
     // staging for SPX_MEM_HOST execution (grow-only)
     spx::DevBuf st_in, st_db, st_wf, st_spec, st_welch, st_max, st_misc, st_flush;
     // large-N (four-step) path, nfft >= 16384
@@ -43,9 +44,9 @@ namespace spx {
 int plan_event(spx_plan* pl, size_t i, cudaEvent_t* out);
 int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long long stream_stride, long long frames,
                        float* db_rows, unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold,
-                       float vmin, float vmax, cudaStream_t st);
+                       float vmin, float vmax, cudaStream_t st, int sys_atomics = 0);
 int bigfft_plan_init(spx_plan* pl);
 int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
                          unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
-                         float vmax, cudaStream_t st);
+                         float vmax, cudaStream_t st, int sys_atomics = 0);
 }  // namespace spx

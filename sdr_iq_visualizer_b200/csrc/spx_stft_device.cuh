@@ -32,6 +32,7 @@ struct StftParams {
     float db_pw_min;             // below this |X|^2 the eps term matters and the exact form is evaluated
     float q_vmin, q_scale;       // u8 = sat(floor((db - vmin) * scale)), scale = 256/(vmax-vmin)
     float q_a, q_b;              // the same map on log2|X|^2:  (db - vmin) * scale = q_a * log2|X|^2 + q_b
+    int sys_atomics;             // accumulators may live on a peer GPU: flush with system-scope atomics
     int frames_per_chunk;        // accumulator flush granularity (<= 256)
     int chunks_per_stream;
     long long total_chunks;
@@ -55,7 +56,11 @@ template <int TUNE>
 SPX_HD float2 ci16_to_f2(unsigned int w) {
 #ifdef __CUDA_ARCH__
     if constexpr ((TUNE & TUNE_I2FP) != 0) {
-        const int lo = (int)__byte_perm(w, 0u, 0x9910), hi = (int)__byte_perm(w, 0u, 0xbb32);
+        // prmt with the sign-replicating selector nibbles (0x8 | byte): bytes {b0, b1, sign(b1), sign(b1)} and
+        // {b2, b3, sign(b3), sign(b3)}.  Inline PTX on purpose: __byte_perm() masks the selector to 3 bits per nibble.
+        int lo, hi;
+        asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(lo) : "r"(w));
+        asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(hi) : "r"(w));
         return make_float2((float)lo, (float)hi);
     }
 #endif
@@ -125,6 +130,21 @@ SPX_HD float quant_pre(float y, float q_a, float q_b) {
     return fmaf(y, q_a, q_b);
 #endif
 }
+
+// accumulator flush: Welch sum (fp64 add) and max-hold (|X|^2 >= 0, so IEEE order == unsigned order).
+// `sys` selects system scope: the target may be another GPU's memory reached over NVLink, reduced into by
+// several GPUs at once (the fused compute + reduction of the multi-GPU configs).
+#ifdef __CUDACC__
+__device__ __forceinline__ void flush_acc(double* welch, float* maxhold, long long o, float sum, float mx, int sys) {
+    if (sys) {
+        if (welch) atomicAdd_system(welch + o, (double)sum);
+        if (maxhold) atomicMax_system(reinterpret_cast<unsigned int*>(maxhold) + o, __float_as_uint(mx));
+    } else {
+        if (welch) atomicAdd(welch + o, (double)sum);
+        if (maxhold) atomicMax(reinterpret_cast<unsigned int*>(maxhold) + o, __float_as_uint(mx));
+    }
+}
+#endif
 
 // ------------------------------------------------------------------ per-thread state
 template <bool ACC>

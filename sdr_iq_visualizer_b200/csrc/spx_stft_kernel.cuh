@@ -196,9 +196,7 @@ __global__ void __launch_bounds__(StftCfg<N>::THREADS, OCC) stft_kernel(const St
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const long long o = (long long)this_stream * N + acc_pos<N>(tid, i);
-                    if (p.welch_acc) atomicAdd(p.welch_acc + o, (double)acc.sum[i]);
-                    // |X|^2 >= 0: IEEE order == unsigned integer order
-                    if (p.maxhold) atomicMax(reinterpret_cast<unsigned int*>(p.maxhold) + o, __float_as_uint(acc.mx[i]));
+                    flush_acc(p.welch_acc, p.maxhold, o, acc.sum[i], acc.mx[i], p.sys_atomics);
                 }
                 acc.reset();
             }

@@ -130,3 +130,61 @@ def sharded_capture_stft(plan, load_samples, n_samples: int, rank: int, world: i
     gathered = gather_rows(rows, gather_to, group) if (wf_rows and gather_to is not None) else None
     return {"welch_acc": welch, "maxhold": mh, "n_frames": total, "rows": gathered, "local_frames": F_local,
             "shard": sh}
+
+
+# ----------------------------------------------------------------------------- fused compute + reduction over peer memory
+class PeerReduceTarget:
+    """The reduction target of a sharded capture, living on rank ``dst`` and mapped into every rank:
+    Welch numerator float64 [1, N], max-hold float32 [1, N] and (optionally) the whole uint8 waterfall
+    [F, N].  Every rank's STFT kernel reduces / writes straight into it over NVLink
+    (``peer_outputs=True``: system-scope atomics, plain remote stores for the rows), so the partial-PSD
+    all-reduce and the row gather are not separate collectives any more -- the transfer overlaps the
+    transform chunk by chunk.  ``torch.distributed`` only carries the 64-byte IPC handles and barriers."""
+
+    def __init__(self, nfft: int, n_frames: int, rank: int, world: int, device: int, dst: int = 0, want_rows: bool = True,
+                 group=None):
+        from . import _native as nat
+        dist = _dist()
+        self.rank, self.world, self.dst, self.device, self.group = rank, world, dst, device, group
+        shapes = {"welch": ((1, nfft), np.float64), "maxhold": ((1, nfft), np.float32)}
+        if want_rows:
+            shapes["rows"] = ((max(n_frames, 1), nfft), np.uint8)
+        self.buffers = {}
+        handles = [None]
+        if rank == dst:
+            for k, (shape, dt) in shapes.items():
+                self.buffers[k] = nat.PeerBuffer(shape, dt, device)
+            handles = [{k: b.handle for k, b in self.buffers.items()}]
+        if world > 1:
+            dist.broadcast_object_list(handles, src=dst, group=group)
+        if rank != dst:
+            for k, (shape, dt) in shapes.items():
+                self.buffers[k] = nat.PeerBuffer.open(handles[0][k], shape, dt, device)
+        self.welch = self.buffers["welch"].view()
+        self.maxhold = self.buffers["maxhold"].view()
+        self.rows = self.buffers["rows"].view() if want_rows else None
+
+    def zero(self) -> None:
+        """Owner clears the accumulators (rows are fully overwritten); call before a barrier."""
+        if self.rank == self.dst:
+            self.buffers["welch"].array.zero_()
+            self.buffers["maxhold"].array.zero_()
+
+    def close(self) -> None:
+        for b in self.buffers.values():
+            b.close()
+        self.buffers = {}
+
+
+def fused_capture_step(plan, d_in, shard: CaptureShard, target: PeerReduceTarget, vmin=-100.0, vmax=0.0) -> int:
+    """One rank's share of a sharded capture with the reduction fused into the kernel: frames
+    [shard.f0, shard.f1) of the device-resident slice ``d_in`` are transformed and their Welch / max-hold
+    partials and uint8 rows land in ``target`` (possibly on another GPU).  Returns the local frame count;
+    the caller synchronises the plan and barriers before the owner reads the result."""
+    F_local = shard.f1 - shard.f0
+    if F_local <= 0:
+        return 0
+    rows = target.rows.rows(shard.f0, shard.f1) if target.rows is not None else False
+    plan.stft(d_in, wf_rows=rows, welch=target.welch, maxhold=target.maxhold, vmin=vmin, vmax=vmax, accumulate=True,
+              n_samples=shard.n_samples, peer_outputs=True)
+    return F_local

@@ -33,6 +33,7 @@ class StreamRing:
         h = C.c_void_p()
         nat.check(nat.lib().spx_ring_create(C.byref(h), plan._h, C.byref(cfg)))
         self._h = h
+        plan._rings.add(self)
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -83,12 +84,15 @@ class SpectralPlan:
         h = C.c_void_p()
         nat.check(nat.lib().spx_plan_create(C.byref(h), C.byref(cfg)))
         self._h = h
+        self._rings = weakref.WeakSet()   # rings borrow the native plan: they are torn down first
         s2, s1 = C.c_double(), C.c_double()
         nat.check(nat.lib().spx_plan_window_sums(self._h, C.byref(s2), C.byref(s1)))
         self.sum_w2, self.sum_w = s2.value, s1.value
 
     # -- lifetime
     def close(self) -> None:
+        for ring in list(getattr(self, "_rings", ())):
+            ring.close()
         h, self._h = getattr(self, "_h", None), None
         if h:
             nat.lib().spx_plan_destroy(h)
@@ -131,7 +135,7 @@ class SpectralPlan:
     def _samples_per_stream(self, x, n_streams: int) -> int:
         if isinstance(x, np.ndarray):
             total = x.size // 2 if (x.dtype == np.int16 or x.dtype == np.float32) else x.size
-        elif isinstance(x, DeviceArray):
+        elif isinstance(x, (DeviceArray, nat.DeviceView)):
             total = x.nbytes // (4 if self.in_fmt == FMT_CI16 else 8)
         else:
             total = x.numel() * x.element_size() // (4 if self.in_fmt == FMT_CI16 else 8)
@@ -140,11 +144,11 @@ class SpectralPlan:
     # -- execution
     def stft(self, x, *, n_streams: int = 1, db_rows=False, wf_rows=False, spectrum=False, welch=False,
              maxhold=False, vmin: float = -100.0, vmax: float = 0.0, accumulate: bool = False,
-             stream: int = 0, n_samples: Optional[int] = None, _time=None) -> StftResult:
+             stream: int = 0, n_samples: Optional[int] = None, peer_outputs: bool = False, _time=None) -> StftResult:
         """Windowed STFT of ``x`` (1 stream, or ``n_streams`` equal-length streams laid out back to
         back).  Each output flag is False (not wanted), True (allocate) or a caller buffer to fill
         (numpy for host input, DeviceArray / CUDA tensor for device input)."""
-        if isinstance(x, np.ndarray) or not (isinstance(x, DeviceArray) or hasattr(x, "data_ptr")):
+        if isinstance(x, np.ndarray) or not (isinstance(x, (DeviceArray, nat.DeviceView)) or hasattr(x, "data_ptr")):
             x = self._host_input(x)
         in_ptr, mem = nat.as_ptr(x)
         L = int(n_samples) if n_samples is not None else self._samples_per_stream(x, n_streams)
@@ -182,6 +186,7 @@ class SpectralPlan:
         a.maxhold = nat.as_ptr(o_mh)[0]
         a.vmin, a.vmax = float(vmin), float(vmax)
         a.stream = stream or None
+        a.peer_outputs = 1 if peer_outputs else 0
         if _time is not None:
             warmup, iters, flush = _time
             ms = (C.c_float * iters)()

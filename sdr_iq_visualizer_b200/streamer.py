@@ -56,6 +56,7 @@ class SDRDataStreamer:
         self.compute_errors = 0
         self.samples_processed = 0
         self.h2d_bytes = 0
+        self._latest = None
 
     # ------------------------------------------------------------------ radio control (host I/O)
     def connect(self):
@@ -212,6 +213,7 @@ class SDRDataStreamer:
 
     def _push(self, data):
         """Bounded queue, drop-oldest when full (streamer.py:186-194)."""
+        self._latest = data
         while True:
             try:
                 self.data_queue.put_nowait(data)
@@ -230,6 +232,12 @@ class SDRDataStreamer:
                 latest = self.data_queue.get_nowait()
             except queue.Empty:
                 return latest
+
+
+    def peek_latest(self):
+        """Newest frame WITHOUT consuming the queue: a second consumer (the chatbot's classify tool,
+        /root/reference/app/chatbot/chatbot.py:149) no longer races the dashboard tick for queue items."""
+        return self._latest
 
 
 # Shared global instance (streamer.py:203)

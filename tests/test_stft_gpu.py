@@ -280,3 +280,32 @@ def test_config5_prefix(sp):
     parity.check_power(r.maxhold[0], P.max(axis=0), what="C5 maxhold")
     parity.check_u8(r.wf_rows, sref.amplitude_db(X), -20.0, 110.0, what="C5 u8")
     pl.close()
+
+
+@pytest.mark.parametrize("nfft,hop,fmt,L", [(4096, 1024, 1, 300_000), (65536, 32768, 0, 1 << 21)])
+def test_peer_output_pipeline_matches_direct_outputs(sp, monkeypatch, nfft, hop, fmt, L):
+    """peer_outputs=True (multi-GPU capture shards): accumulators reduced with system-scope atomics, uint8 rows
+    staged in frame pieces and pushed by the copy engine -- same rows and sums as the direct path.  World size 1
+    here (the target is this GPU's own memory); tools/bench_sharded.py --check covers the IPC-mapped case."""
+    from sdr_iq_visualizer_b200 import _native as nat, dist as sd
+    monkeypatch.setenv("SPX_PEER_PIECE_BYTES", str(40 * nfft))           # 40-frame pieces: several pieces, ragged tail
+    x = sref.synth_iq(L, seed=9)
+    x = sref.to_ci16(x) if fmt else x.astype(np.complex64)
+    pl = sp.SpectralPlan(nfft, hop, "hann", fmt)
+    ref = pl.stft(x, wf_rows=True, welch=True, maxhold=True, vmin=-20.0, vmax=130.0)
+    F = ref.n_frames
+    d_in = nat.DeviceArray.from_host(x)
+    sh = sd.capture_shard(L, nfft, hop, 0, 1)
+    assert (sh.f0, sh.f1) == (0, F)
+    tgt = sd.PeerReduceTarget(nfft, F, 0, 1, 0)
+    for _ in range(2):                                                     # second pass reuses staging buffers and events
+        tgt.zero()
+        assert sd.fused_capture_step(pl, d_in, sh, tgt, -20.0, 130.0) == F
+        pl.sync()
+        rows = np.empty((F, nfft), np.uint8)
+        nat.check(nat.lib().spx_memcpy_d2h(0, rows.ctypes.data, tgt.rows.ptr, rows.nbytes))
+        np.testing.assert_array_equal(rows, ref.wf_rows)
+        np.testing.assert_allclose(tgt.buffers["welch"].array.to_host(), ref.welch_acc, rtol=1e-12)
+        np.testing.assert_array_equal(tgt.buffers["maxhold"].array.to_host(), ref.maxhold)
+    tgt.close()
+    pl.close()

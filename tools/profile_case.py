@@ -18,6 +18,12 @@ if case == "c2":
     F = pl.frame_count(L)
     kw = dict(wf_rows=nat.DeviceArray((F, 4096), np.uint8), welch=nat.DeviceArray((1, 4096), np.float64),
               maxhold=nat.DeviceArray((1, 4096), np.float32), vmin=20.0, vmax=130.0)
+elif case == "c5":
+    x = nat.DeviceArray.from_host(rng.standard_normal(2 * L).astype(np.float32).view(np.complex64))
+    pl = sp.SpectralPlan(65536, 32768, "hann", sp.FMT_CF32, variant=variant)
+    F = pl.frame_count(L)
+    kw = dict(wf_rows=nat.DeviceArray((F, 65536), np.uint8), welch=nat.DeviceArray((1, 65536), np.float64),
+              maxhold=nat.DeviceArray((1, 65536), np.float32), vmin=-20.0, vmax=110.0)
 else:
     x = nat.DeviceArray.from_host(rng.standard_normal(2 * L).astype(np.float32).view(np.complex64))
     pl = sp.SpectralPlan(4096, 4096, "hann", sp.FMT_CF32, variant=variant)
