@@ -161,6 +161,10 @@ SPX_API int spx_stft_time(spx_plan* plan, spx_stft_args* args, int32_t warmup, i
 SPX_API int spx_welch_finalize(spx_plan* plan, int32_t mem, const double* welch_acc, int64_t n_frames, double fs,
                        double* pxx, double* pxx_db, void* stream);
 
+/* The same for `n_streams` accumulators laid out [n_streams][nfft] (one launch; every stream has n_frames frames). */
+SPX_API int spx_welch_finalize_batch(spx_plan* plan, int32_t mem, const double* welch_acc, int32_t n_streams,
+                                     int64_t n_frames, double fs, double* pxx, double* pxx_db, void* stream);
+
 /* The plan's compute stream (cudaStream_t), so that callers can order their own SPX_MEM_DEVICE calls
  * (spx_welch_finalize, spx_classify_features, spx_timer_*) after the plan's kernels. */
 SPX_API int spx_plan_stream(spx_plan* plan, void** stream_out);

@@ -111,6 +111,8 @@ _SIGNATURES = {
                                 C.POINTER(C.c_float)]),
     "spx_welch_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
+    "spx_welch_finalize_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
     "spx_classify_features": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                         C.POINTER(spx_features), C.c_void_p, C.c_int32, C.POINTER(spx_feature_opts),
                                         C.c_void_p]),

@@ -231,15 +231,43 @@ static int stft_exec_host(spx_plan* pl, spx_stft_args* a, long long F) {
 // traffic).  The uint8 rows are produced in frame pieces into two local staging buffers and pushed to the peer by
 // the copy engine on `s_d2h` while the next piece is being transformed: full-size NVLink writes instead of the
 // kernel's 16..32-byte row fragments, and the transfer hides behind the transform piece by piece.
+// last hop of the hierarchical reduction (registers -> this GPU's L2 -> the owner's HBM over NVLink)
+__global__ void peer_reduce_kernel(const double* __restrict__ w_local, const float* __restrict__ m_local, double* w_peer,
+                                   float* m_peer, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        flush_acc(w_local ? w_peer : nullptr, m_local ? m_peer : nullptr, i, 0.f, 0.f, -1, w_local ? w_local[i] : 0.0,
+                  m_local ? m_local[i] : 0.f);
+}
+
 static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cudaStream_t st) {
     const int N = pl->cfg.nfft, hop = pl->cfg.hop;
     const size_t elt = in_elt(pl);
     const long long S = a->n_streams;
+    // partials accumulate in local memory (device-scope atomics in L2); one system-scope pass at the end adds them
+    // to the owner's buffers: S*N remote atomics per call instead of one per chunk flush
+    double* w_local = nullptr;
+    float* m_local = nullptr;
+    if (a->welch_acc) {
+        SPX_TRY(pl->st_welch.reserve((size_t)S * N * sizeof(double)));
+        w_local = (double*)pl->st_welch.ptr;
+        SPX_CUDA(cudaMemsetAsync(w_local, 0, (size_t)S * N * sizeof(double), st));
+    }
+    if (a->maxhold) {
+        SPX_TRY(pl->st_max.reserve((size_t)S * N * sizeof(float)));
+        m_local = (float*)pl->st_max.ptr;
+        SPX_CUDA(cudaMemsetAsync(m_local, 0, (size_t)S * N * sizeof(float), st));
+    }
     long long piece = (long long)(pl->peer_piece_bytes / (size_t)N);
     if (piece < 1) piece = 1;
     if (piece > F) piece = F;
-    SPX_TRY(pl->st_wf.reserve((size_t)(2 * piece) * N));
-    unsigned char* stage[2] = {(unsigned char*)pl->st_wf.ptr, (unsigned char*)pl->st_wf.ptr + (size_t)piece * N};
+    unsigned char* stage[2] = {nullptr, nullptr};
+    if (a->wf_rows) {
+        SPX_TRY(pl->st_wf.reserve((size_t)(2 * piece) * N));
+        stage[0] = (unsigned char*)pl->st_wf.ptr;
+        stage[1] = stage[0] + (size_t)piece * N;
+    } else {
+        piece = F;  // nothing to stage: one launch per stream
+    }
     cudaEvent_t e_k[2], e_c[2];
     for (int i = 0; i < 2; ++i) {
         SPX_TRY(plan_event(pl, (size_t)i, &e_k[i]));
@@ -251,19 +279,28 @@ static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cu
         for (long long f_lo = 0; f_lo < F; f_lo += piece, ++idx) {
             const long long nf = F - f_lo < piece ? F - f_lo : piece;
             const int b = (int)(idx & 1);
-            if (idx >= 2) SPX_CUDA(cudaStreamWaitEvent(st, e_c[b], 0));   // the copy that last used this buffer is done
+            if (idx >= 2 && a->wf_rows) SPX_CUDA(cudaStreamWaitEvent(st, e_c[b], 0));   // the copy that last used this buffer is done
             SPX_TRY(stft_launch_device(pl, in_s + (size_t)(f_lo * hop) * elt, 1, 0, nf, nullptr, stage[b], nullptr,
-                                       a->welch_acc ? a->welch_acc + s * N : nullptr, a->maxhold ? a->maxhold + s * N : nullptr,
-                                       a->vmin, a->vmax, st, 1));
+                                       w_local ? w_local + s * N : nullptr, m_local ? m_local + s * N : nullptr,
+                                       a->vmin, a->vmax, st, 0));
+            if (!a->wf_rows) continue;
             SPX_CUDA(cudaEventRecord(e_k[b], st));
             SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, e_k[b], 0));
             SPX_CUDA(cudaMemcpyAsync(a->wf_rows + (size_t)(s * F + f_lo) * N, stage[b], (size_t)nf * N, cudaMemcpyDefault, pl->s_d2h));
             SPX_CUDA(cudaEventRecord(e_c[b], pl->s_d2h));
         }
     }
+    if (w_local || m_local) {
+        const long long n = S * N;
+        peer_reduce_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(w_local, m_local, a->welch_acc,
+                                                                                                     a->maxhold, n);
+        SPX_CUDA(cudaGetLastError());
+    }
     // whoever waits on `st` (spx_plan_sync, a later launch) also waits for the last copies
-    SPX_CUDA(cudaStreamWaitEvent(st, e_c[0], 0));
-    if (idx >= 2) SPX_CUDA(cudaStreamWaitEvent(st, e_c[1], 0));
+    if (a->wf_rows) {
+        SPX_CUDA(cudaStreamWaitEvent(st, e_c[0], 0));
+        if (idx >= 2) SPX_CUDA(cudaStreamWaitEvent(st, e_c[1], 0));
+    }
     a->d2h_bytes_out = 0;
     return SPX_OK;
 }
@@ -566,7 +603,7 @@ int spx_stft_exec(spx_plan* pl, spx_stft_args* a) {
             if (a->welch_acc) SPX_CUDA(cudaMemsetAsync(a->welch_acc, 0, (size_t)S * N * sizeof(double), st));
             if (a->maxhold) SPX_CUDA(cudaMemsetAsync(a->maxhold, 0, (size_t)S * N * sizeof(float), st));
         }
-        if (a->peer_outputs && a->wf_rows && !a->db_rows && !a->spec_rows && F > 0) return stft_exec_device_peer(pl, a, F, st);
+        if (a->peer_outputs && !a->db_rows && !a->spec_rows && F > 0) return stft_exec_device_peer(pl, a, F, st);
         return stft_launch_device(pl, a->in, S, a->stream_stride, F, a->db_rows, a->wf_rows,
                                   reinterpret_cast<float2*>(a->spec_rows), a->welch_acc, a->maxhold, a->vmin, a->vmax, st,
                                   a->peer_outputs ? 1 : 0);
@@ -611,11 +648,16 @@ int spx_stft_time(spx_plan* pl, spx_stft_args* a, int32_t warmup, int32_t iters,
 
 int spx_welch_finalize(spx_plan* pl, int32_t mem, const double* welch_acc, int64_t n_frames, double fs, double* pxx,
                        double* pxx_db, void* stream) {
+    return spx_welch_finalize_batch(pl, mem, welch_acc, 1, n_frames, fs, pxx, pxx_db, stream);
+}
+
+int spx_welch_finalize_batch(spx_plan* pl, int32_t mem, const double* welch_acc, int32_t n_streams, int64_t n_frames,
+                             double fs, double* pxx, double* pxx_db, void* stream) {
     if (!pl || !welch_acc) return spx_set_error(SPX_E_INVALID, "NULL argument");
-    if (n_frames < 1 || !(fs > 0)) return spx_set_error(SPX_E_INVALID, "n_frames and fs must be positive");
+    if (n_frames < 1 || !(fs > 0) || n_streams < 1) return spx_set_error(SPX_E_INVALID, "n_frames, fs and n_streams must be positive");
     std::lock_guard<std::mutex> g(pl->mu);
     SPX_CUDA(cudaSetDevice(pl->cfg.device));
-    const int N = pl->cfg.nfft;
+    const int N = pl->cfg.nfft * n_streams;  // element-wise: the batch is one long array
     // mlab.psd: |X|^2 / (Fs * sum(w^2)), mean over frames.  in_scale is part of the data, not of the window.
     const double inv = 1.0 / ((double)n_frames * fs * pl->sum_w2);
     if (mem == SPX_MEM_DEVICE) {

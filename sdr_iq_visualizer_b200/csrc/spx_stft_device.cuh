@@ -135,8 +135,12 @@ SPX_HD float quant_pre(float y, float q_a, float q_b) {
 // `sys` selects system scope: the target may be another GPU's memory reached over NVLink, reduced into by
 // several GPUs at once (the fused compute + reduction of the multi-GPU configs).
 #ifdef __CUDACC__
-__device__ __forceinline__ void flush_acc(double* welch, float* maxhold, long long o, float sum, float mx, int sys) {
-    if (sys) {
+__device__ __forceinline__ void flush_acc(double* welch, float* maxhold, long long o, float sum, float mx, int sys,
+                                          double sum64 = 0.0, float mx32 = 0.f) {
+    if (sys < 0) {  // system scope with a float64 addend (the final local -> peer pass)
+        if (welch) atomicAdd_system(welch + o, sum64);
+        if (maxhold) atomicMax_system(reinterpret_cast<unsigned int*>(maxhold) + o, __float_as_uint(mx32));
+    } else if (sys) {
         if (welch) atomicAdd_system(welch + o, (double)sum);
         if (maxhold) atomicMax_system(reinterpret_cast<unsigned int*>(maxhold) + o, __float_as_uint(mx));
     } else {

@@ -211,19 +211,21 @@ class SpectralPlan:
         nat.check(nat.lib().spx_plan_stream(self._h, C.byref(st)))
         return int(st.value or 0)
 
-    def welch_finalize(self, welch_acc, n_frames: int, sample_rate: float, want_db: bool = True, pxx=None, pdb=None):
-        """mlab.psd density and its dB from an accumulated numerator (one stream).  ``pxx`` / ``pdb`` may be
-        caller buffers (same memory space as ``welch_acc``) to avoid an allocation per call."""
+    def welch_finalize(self, welch_acc, n_frames: int, sample_rate: float, want_db: bool = True, pxx=None, pdb=None,
+                       n_streams: int = 1):
+        """mlab.psd density and its dB from an accumulated numerator (``n_streams`` accumulators laid out
+        [n_streams][nfft], one launch).  ``pxx`` / ``pdb`` may be caller buffers (same memory space as
+        ``welch_acc``) to avoid an allocation per call."""
         p, mem = nat.as_ptr(welch_acc)
-        N = self.nfft
+        N = self.nfft * int(n_streams)
         if mem == MEM_HOST:
             pxx = np.empty(N, np.float64) if pxx is None else pxx
             pdb = (np.empty(N, np.float64) if want_db else None) if pdb is None else pdb
         else:
             pxx = DeviceArray((N,), np.float64, self.device) if pxx is None else pxx
             pdb = (DeviceArray((N,), np.float64, self.device) if want_db else None) if pdb is None else pdb
-        nat.check(nat.lib().spx_welch_finalize(self._h, mem, p, int(n_frames), float(sample_rate), nat.as_ptr(pxx)[0],
-                                               nat.as_ptr(pdb)[0], None))
+        nat.check(nat.lib().spx_welch_finalize_batch(self._h, mem, p, int(n_streams), int(n_frames), float(sample_rate),
+                                                     nat.as_ptr(pxx)[0], nat.as_ptr(pdb)[0], None))
         return pxx, pdb
 
 

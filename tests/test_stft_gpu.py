@@ -305,7 +305,7 @@ def test_peer_output_pipeline_matches_direct_outputs(sp, monkeypatch, nfft, hop,
         rows = np.empty((F, nfft), np.uint8)
         nat.check(nat.lib().spx_memcpy_d2h(0, rows.ctypes.data, tgt.rows.ptr, rows.nbytes))
         np.testing.assert_array_equal(rows, ref.wf_rows)
-        np.testing.assert_allclose(tgt.buffers["welch"].array.to_host(), ref.welch_acc, rtol=1e-12)
+        np.testing.assert_allclose(tgt.buffers["welch"].array.to_host(), ref.welch_acc, rtol=1e-6)  # fp32 partials regroup with the pieces
         np.testing.assert_array_equal(tgt.buffers["maxhold"].array.to_host(), ref.maxhold)
     tgt.close()
     pl.close()

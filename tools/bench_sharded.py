@@ -187,15 +187,23 @@ def main():
             barrier()
             if ns:
                 pl.stft(d_in, n_streams=ns, welch=d_we, n_samples=Ls)
-                for i in range(ns):
-                    pl.welch_finalize(nat.DeviceView(d_we.ptr + i * N * 8, (N,), np.float64, dev), F, 61.44e6,
-                                      pxx=nat.DeviceView(d_pxx.ptr + i * N * 8, (N,), np.float64, dev),
-                                      pdb=nat.DeviceView(d_pdb.ptr + i * N * 8, (N,), np.float64, dev))
+                pl.welch_finalize(d_we, F, 61.44e6, pxx=d_pxx, pdb=d_pdb, n_streams=ns)
                 mine = features.measure_batch(d_pdb, n=N, batch=ns, device=dev, stream=pl.stream, want_peaks=False)
             else:
                 mine = []
-            feats[0] = sd.allgather_objects([(m["snr_db"], m["last_20db"] - m["first_20db"], m["peak_count"]) for m in mine]) \
-                if world > 1 else [mine]
+            # per-stream features (SNR, 3/10/20 dB occupied-bandwidth bins, flatness, kurtosis, peak count) -> every rank
+            packed = torch.tensor([[m["snr_db"], m["last_3db"] - m["first_3db"], m["last_10db"] - m["first_10db"],
+                                    m["last_20db"] - m["first_20db"], m["flatness"], m["kurtosis"], m["peak_count"]] for m in mine],
+                                  dtype=torch.float64, device=f"cuda:{local}").reshape(-1, 7)
+            if world > 1:
+                per = -(-S // world)
+                pad = torch.zeros((per, 7), dtype=torch.float64, device=f"cuda:{local}")
+                pad[: packed.shape[0]] = packed
+                allf = torch.empty((world * per, 7), dtype=torch.float64, device=f"cuda:{local}")
+                dist.all_gather_into_tensor(allf, pad)
+                feats[0] = [allf[r * per: r * per + (sd.stream_block(S, r, world)[1] - sd.stream_block(S, r, world)[0])] for r in range(world)]
+            else:
+                feats[0] = [packed]
             barrier()
 
         for _ in range(args.warmup):

@@ -7,7 +7,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/tests_${tag}.log 2>&1; echo "py
 run $G --config c5 --collective fused --log2-samples 25 --steps 2 --check
 run $G --config c5 --collective nccl --log2-samples 25 --steps 2 --check
 run $G --config c4 --log2-samples 22 --steps 2 --check
-for g in 1 $G; do
+for g in $G; do
   run $g --config c5 --collective fused --steps 5
   run $g --config c5 --collective nccl --steps 5
   run $g --config c4 --steps 5
