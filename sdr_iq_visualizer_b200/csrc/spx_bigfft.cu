@@ -43,7 +43,7 @@ struct BigParams {
     float2* spec_rows;
     double* welch_acc;       // [N] of this stream
     float* maxhold;
-    float db_eps, db_pw_min, q_vmin, q_scale;
+    float db_eps, db_pw_min, q_vmin, q_scale, q_a, q_b;
     int frames_per_chunk;    // kernel B: accumulator flush granularity
     int sys_atomics;         // accumulators may live on a peer GPU
 };
@@ -58,78 +58,115 @@ struct BigCfg {
     static constexpr int P1 = plan_passes(N1);
     static constexpr int BUF1 = padded_size(N1) + (P1 >= 3 ? N1 : 0);
     static constexpr int S1 = BUF1 | 1;                        // odd column stride: conflict-free across columns
+    static constexpr int TW1 = plan_tw_size(N1);
     // kernel B
     static constexpr int T2 = N2 / 16;
-    static constexpr int FPC = N2 >= 1024 ? 8 : (256 / T2 > 32 ? 32 : 256 / T2);  // rows per CTA
+    static constexpr int FPC = N2 >= 1024 ? 4 : (256 / T2 > 32 ? 32 : 256 / T2);  // rows per CTA
     static constexpr int THREADS_B = FPC * T2;
     static constexpr int P2 = plan_passes(N2);
     static constexpr int BUF2 = padded_size(N2) + (P2 >= 3 ? N2 : 0);
+    static constexpr int TW2 = plan_tw_size(N2);
     static constexpr int TILE_LD = FPC + 1;                    // padded tile row (floats)
+    // shared memory (bytes): [exchange buffers][twiddle table][staging of the next frame][dB tile (B only)]
+    static constexpr size_t smem_a(int elt) { return (size_t)(G * S1 + TW1) * 8 + (size_t)N1 * G * elt; }
+    static constexpr size_t smem_b() { return (size_t)(FPC * BUF2 + TW2) * 8 + (size_t)FPC * N2 * 8 + (size_t)N2 * TILE_LD * 4; }
 };
 
+// ---- cp.async (LDGSTS): every thread prefetches exactly the elements it will read back itself, so the staging
+// buffer needs no barrier -- it is a register-free prefetch of the next frame that overlaps the current transform
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ------------------------------------------------------------------ kernel A: column FFTs + twiddle
+// A CTA owns one group of G adjacent columns for all its frames (grid = groups x frame lanes), so the window
+// values and the W_N^{n2 k1} twiddles of a thread are frame-invariant and live in registers.
 template <int N1, int N2, int FMT>
 __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A) big_cols_kernel(const BigParams p) {
     using C = BigCfg<N1, N2>;
     constexpr int N = C::N, T1 = C::T1, G = C::G, P = C::P1;
+    constexpr int ELT = FMT == FMT_CF32 ? 8 : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* smem = reinterpret_cast<float2*>(smem_raw);
+    float2* tws = smem + G * C::S1;
+    unsigned char* stage = smem_raw + (size_t)(G * C::S1 + C::TW1) * 8;
     const int c = threadIdx.x % G;     // column inside the group (fast lane index -> coalesced rows)
     const int tid = threadIdx.x / G;   // position inside the N1-point FFT
     float2* bufA = smem + c * C::S1;
     float2* bufB = bufA + padded_size(N1);
     constexpr int GROUPS = N2 / G;
-    const long long items = (long long)p.frames * GROUPS;
-    float2 v[16];
-    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-        const int f = (int)(it / GROUPS);
-        const int n2 = (int)(it - (long long)f * GROUPS) * G + c;
-        const long long s0 = p.sample0 + (long long)f * p.hop;
-        // pass 0 input: x[N2*(tid + t*T1) + n2], window fused
+    const int g = blockIdx.x % GROUPS;
+    const int lane_f = blockIdx.x / GROUPS, lanes_f = gridDim.x / GROUPS;   // host: gridDim.x is a multiple of GROUPS
+    const int n2 = g * G + c;
+    for (int i = threadIdx.x; i < C::TW1; i += C::THREADS_A) tws[i] = __ldg(p.tw1 + i);
+
+    constexpr int SL = P - 1, RL = plan_radix(N1, SL), NB = 16 / RL;
+    float w[16];
+    float2 wn[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) w[t] = p.win ? __ldg(p.win + N2 * (tid + t * T1) + n2) : 1.0f;
+#pragma unroll
+    for (int u = 0; u < NB; ++u)
+#pragma unroll
+        for (int t = 0; t < RL; ++t) {
+            const int k1 = tid + T1 * u + t * (N1 / RL);
+            const unsigned m = ((unsigned)n2 * (unsigned)k1) & (unsigned)(N - 1);
+            wn[u * RL + t] = cmul(__ldg(p.wn_coarse + (m >> 8)), __ldg(p.wn_fine + (m & 255u)));
+        }
+    const char* in_bytes = reinterpret_cast<const char*>(p.in);
+    auto prefetch = [&](int f) {
+        const char* src = in_bytes + (size_t)(p.sample0 + (long long)f * p.hop + n2) * ELT;
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-            const int i = N2 * (tid + t * T1) + n2;
-            if (FMT == FMT_CF32) v[t] = ld_stream_cf32(reinterpret_cast<const float2*>(p.in) + s0 + i);
-            else                 v[t] = ld_stream_ci16<TUNE_I2FP>(reinterpret_cast<const short2*>(p.in) + s0 + i);
+            const int row = tid + t * T1;
+            if (FMT == FMT_CF32) cp_async8(stage + (size_t)(row * G + c) * ELT, src + (size_t)N2 * row * ELT);
+            else                 cp_async4(stage + (size_t)(row * G + c) * ELT, src + (size_t)N2 * row * ELT);
         }
-        if (p.win != nullptr) {
+    };
+    if (lane_f < p.frames) prefetch(lane_f);
+    __syncthreads();  // twiddle table visible
+    float2 v[16];
+    for (int f = lane_f; f < p.frames; f += lanes_f) {
+        cp_async_wait_all();
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const float w = ld_keep(p.win + N2 * (tid + t * T1) + n2);
-                v[t].x *= w;
-                v[t].y *= w;
-            }
+        for (int t = 0; t < 16; ++t) {
+            const int row = tid + t * T1;
+            float2 x;
+            if (FMT == FMT_CF32) x = reinterpret_cast<const float2*>(stage)[row * G + c];
+            else                 x = ci16_to_f2<TUNE_I2FP>(reinterpret_cast<const unsigned int*>(stage)[row * G + c]);
+            v[t] = make_float2(x.x * w[t], x.y * w[t]);
         }
+        if (f + lanes_f < p.frames) prefetch(f + lanes_f);   // own slots only: overlaps the whole transform below
         pass_dft<N1, 0>(v);
         if constexpr (P > 1) {
             pass_store_smem<N1, 0>(v, tid, bufA);
             __syncthreads();
             pass_load_smem<N1, 1>(v, tid, bufA);
-            pass_twiddle_table<N1, 1, false>(v, tid, p.tw1);
+            pass_twiddle_table<N1, 1, true>(v, tid, tws);
             pass_dft<N1, 1>(v);
         }
         if constexpr (P > 2) {
             pass_store_smem<N1, 1>(v, tid, bufB);
             __syncthreads();
             pass_load_smem<N1, 2>(v, tid, bufB);
-            pass_twiddle_table<N1, 2, false>(v, tid, p.tw1);
+            pass_twiddle_table<N1, 2, true>(v, tid, tws);
             pass_dft<N1, 2>(v);
         }
         static_assert(P <= 3, "N1 up to 4096");
         // twiddle W_N^{n2*k1} and store T[k1][n2]
-        constexpr int SL = P - 1, RL = plan_radix(N1, SL), NB = 16 / RL;
         float2* trow = p.scratch + (long long)f * N + n2;
 #pragma unroll
-        for (int u = 0; u < NB; ++u) {
+        for (int u = 0; u < NB; ++u)
 #pragma unroll
             for (int t = 0; t < RL; ++t) {
                 const int k1 = tid + T1 * u + t * (N1 / RL);
-                const unsigned m = ((unsigned)n2 * (unsigned)k1) & (unsigned)(N - 1);
-                const float2 w = cmul(ld_keep(p.wn_coarse + (m >> 8)), ld_keep(p.wn_fine + (m & 255u)));
-                trow[(long long)k1 * N2] = cmul(v[u * RL + t], w);
+                trow[(long long)k1 * N2] = cmul(v[u * RL + t], wn[u * RL + t]);
             }
-        }
-        if constexpr (P > 1) __syncthreads();  // buffers are rewritten by the next item
+        if constexpr (P > 1) __syncthreads();  // exchange buffers are rewritten by the next frame
     }
 }
 
@@ -140,18 +177,30 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(con
     constexpr int N = C::N, T2 = C::T2, FPC = C::FPC, P = C::P2, LD = C::TILE_LD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* smem = reinterpret_cast<float2*>(smem_raw);
-    float* tile = reinterpret_cast<float*>(smem_raw);            // aliases the exchange buffers (after a barrier)
+    float2* tws = smem + FPC * C::BUF2;
+    float2* stage = tws + C::TW2;                                  // [FPC][N2] next frame's rows
+    float* tile = reinterpret_cast<float*>(stage + FPC * N2);      // [N2][LD] log2-power tile for the transposed store
     const int slot = threadIdx.x / T2;
     const int tid = threadIdx.x - slot * T2;
     float2* bufA = smem + slot * C::BUF2;
     float2* bufB = bufA + padded_size(N2);
+    float2* my_stage = stage + slot * N2;
+    for (int i = threadIdx.x; i < C::TW2; i += C::THREADS_B) tws[i] = __ldg(p.tw2 + i);
     constexpr int GROUPS = N1 / FPC;
     const int chunks = (p.frames + p.frames_per_chunk - 1) / p.frames_per_chunk;
     const long long items = (long long)GROUPS * chunks;
     constexpr int SL = P - 1, RL = plan_radix(N2, SL), NB = 16 / RL;
+    auto prefetch = [&](long long it, int f) {   // rows of frame f for item `it` (its row group)
+        const int gg = (int)(it % GROUPS);
+        const float2* row = p.scratch + (long long)f * N + (long long)(gg * FPC + slot) * N2;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) cp_async8(my_stage + tid + t * T2, row + tid + t * T2);
+    };
     StftAcc<ACC> acc;
     acc.reset();
     float2 v[16];
+    if ((long long)blockIdx.x < items) prefetch(blockIdx.x, (int)(blockIdx.x / GROUPS) * p.frames_per_chunk);
+    __syncthreads();
     for (long long it = blockIdx.x; it < items; it += gridDim.x) {
         const int g = (int)(it % GROUPS);        // consecutive CTAs take consecutive row groups of the same frames
         const int ch = (int)(it / GROUPS);
@@ -159,22 +208,25 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(con
         const int f_lo = ch * p.frames_per_chunk;
         const int f_hi = min(p.frames, f_lo + p.frames_per_chunk);
         for (int f = f_lo; f < f_hi; ++f) {
-            const float2* row = p.scratch + (long long)f * N + (long long)k1 * N2;
+            cp_async_wait_all();
 #pragma unroll
-            for (int t = 0; t < 16; ++t) v[t] = row[tid + t * T2];
+            for (int t = 0; t < 16; ++t) v[t] = my_stage[tid + t * T2];
+            // next frame of this item, or the first frame of this CTA's next item
+            if (f + 1 < f_hi) prefetch(it, f + 1);
+            else if (it + gridDim.x < items) prefetch(it + gridDim.x, (int)((it + gridDim.x) / GROUPS) * p.frames_per_chunk);
             pass_dft<N2, 0>(v);
             if constexpr (P > 1) {
                 pass_store_smem<N2, 0>(v, tid, bufA);
                 __syncthreads();
                 pass_load_smem<N2, 1>(v, tid, bufA);
-                pass_twiddle_table<N2, 1, false>(v, tid, p.tw2);
+                pass_twiddle_table<N2, 1, true>(v, tid, tws);
                 pass_dft<N2, 1>(v);
             }
             if constexpr (P > 2) {
                 pass_store_smem<N2, 1>(v, tid, bufB);
                 __syncthreads();
                 pass_load_smem<N2, 2>(v, tid, bufB);
-                pass_twiddle_table<N2, 2, false>(v, tid, p.tw2);
+                pass_twiddle_table<N2, 2, true>(v, tid, tws);
                 pass_dft<N2, 2>(v);
             }
             static_assert(P <= 3, "N2 up to 4096");
@@ -199,10 +251,17 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(con
                 }
             }
             if (p.db_rows || p.wf_rows) {
+                // y = log2 of the (eps-corrected) power; one uniform branch per thread as in K1's epilogue
+                float pmin = v[0].x;
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    v[i].y = v[i].x >= p.db_pw_min ? amp_db_fast(v[i].x) : amp_db_exact(v[i].x, p.db_eps);
-                __syncthreads();  // every thread is done reading the exchange buffers: reuse them as the tile
+                for (int i = 1; i < 16; ++i) pmin = fminf(pmin, v[i].x);
+                if (pmin >= p.db_pw_min) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i].y = fast_log2(v[i].x);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i].y = 2.0f * fast_log2(fast_sqrt(v[i].x) + p.db_eps);
+                }
 #pragma unroll
                 for (int u = 0; u < NB; ++u)
 #pragma unroll
@@ -211,19 +270,36 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(con
                         tile[k2s * LD + slot] = v[u * RL + t].y;
                     }
                 __syncthreads();
-                // copy out: runs of FPC consecutive bins k1_0 .. k1_0+FPC-1 for every k2
+                // copy out: for every k2 a run of FPC consecutive bins k1_0 .. k1_0+FPC-1, written as 8-bin vectors
                 const int k1_0 = g * FPC;
-                for (int idx = threadIdx.x; idx < FPC * N2; idx += C::THREADS_B) {
-                    const int j = idx % FPC, k2s = idx / FPC;
-                    const float db = tile[k2s * LD + j];
-                    const long long o = orow + k1_0 + j + (long long)N1 * k2s;
-                    if (p.db_rows) p.db_rows[o] = db;
-                    if (p.wf_rows) p.wf_rows[o] = (unsigned char)sat_floor_u8((db - p.q_vmin) * p.q_scale);
+                constexpr int VW = FPC >= 8 ? 8 : 4, NV = FPC / VW;
+                for (int idx = threadIdx.x; idx < N2 * NV; idx += C::THREADS_B) {
+                    const int j0 = (idx % NV) * VW, k2s = idx / NV;
+                    float y[VW];
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) y[q] = tile[k2s * LD + j0 + q];
+                    const long long o = orow + k1_0 + j0 + (long long)N1 * k2s;
+                    if (p.db_rows) {
+                        constexpr float K = 0.5f * SPX_DB_PER_LOG2;
+#pragma unroll
+                        for (int q = 0; q < VW; q += 4)
+                            *reinterpret_cast<float4*>(p.db_rows + o + q) = make_float4(K * y[q], K * y[q + 1], K * y[q + 2], K * y[q + 3]);
+                    }
+                    if (p.wf_rows) {
+                        unsigned int wd[VW / 4];
+#pragma unroll
+                        for (int h = 0; h < VW / 4; ++h) {
+                            wd[h] = 0u;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) wd[h] |= sat_floor_u8(quant_pre(y[4 * h + q], p.q_a, p.q_b)) << (8 * q);
+                        }
+                        if constexpr (VW == 8) *reinterpret_cast<uint2*>(p.wf_rows + o) = make_uint2(wd[0], wd[1]);
+                        else *reinterpret_cast<unsigned int*>(p.wf_rows + o) = wd[0];
+                    }
                 }
-                __syncthreads();  // tile is overwritten by the next frame's pass 0
-            } else if constexpr (P > 1) {
-                __syncthreads();
+                // no barrier here: the next write of `tile` comes after the next frame's exchange barrier
             }
+            if constexpr (P > 1) __syncthreads();  // exchange buffers (and the tile) are reused by the next frame
         }
         if constexpr (ACC) {
 #pragma unroll
@@ -285,38 +361,51 @@ template <int N1, int N2>
 static int big_launch_pair(spx_plan* pl, BigParams& p, cudaStream_t st) {
     using C = BigCfg<N1, N2>;
     const bool acc = p.welch_acc != nullptr || p.maxhold != nullptr;
-    const size_t smem_a = (size_t)C::G * C::S1 * sizeof(float2);
-    const size_t smem_b_buf = (size_t)C::FPC * C::BUF2 * sizeof(float2);
-    const size_t smem_b_tile = (size_t)N2 * C::TILE_LD * sizeof(float);
-    const size_t smem_b = smem_b_buf > smem_b_tile ? smem_b_buf : smem_b_tile;
+    const bool cf32 = pl->cfg.in_fmt == SPX_FMT_CF32;
+    const size_t smem_a = C::smem_a(cf32 ? 8 : 4);
+    const size_t smem_b = C::smem_b();
     auto ka_c = big_cols_kernel<N1, N2, FMT_CF32>;
     auto ka_i = big_cols_kernel<N1, N2, FMT_CI16>;
     auto kb_a = big_rows_kernel<N1, N2, true>;
     auto kb_n = big_rows_kernel<N1, N2, false>;
-    static bool configured[64] = {false};
+    static int occ_a[64][2] = {{0}}, occ_b[64][2] = {{0}};   // per device, benign race (same values)
     int dev = 0;
     SPX_CUDA(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        SPX_CUDA(cudaFuncSetAttribute(ka_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-        SPX_CUDA(cudaFuncSetAttribute(ka_i, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    dev &= 63;
+    if (occ_a[dev][0] == 0) {
+        SPX_CUDA(cudaFuncSetAttribute(ka_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_a(8)));
+        SPX_CUDA(cudaFuncSetAttribute(ka_i, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_a(4)));
         SPX_CUDA(cudaFuncSetAttribute(kb_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         SPX_CUDA(cudaFuncSetAttribute(kb_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        configured[dev & 63] = true;
+        int o[4] = {0, 0, 0, 0};
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[0], ka_c, C::THREADS_A, C::smem_a(8)));
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[1], ka_i, C::THREADS_A, C::smem_a(4)));
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[2], kb_a, C::THREADS_B, smem_b));
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[3], kb_n, C::THREADS_B, smem_b));
+        for (int i = 0; i < 4; ++i)
+            if (o[i] < 1) return spx_set_error(SPX_E_CUDA, "large-N kernel does not fit on an SM (N1=%d N2=%d)", N1, N2);
+        occ_a[dev][1] = o[1]; occ_b[dev][0] = o[2]; occ_b[dev][1] = o[3];
+        occ_a[dev][0] = o[0];
     }
-    const long long items_a = (long long)p.frames * (N2 / C::G);
-    long long grid_a = items_a < (long long)pl->sm_count * 4 ? items_a : (long long)pl->sm_count * 4;
-    if (pl->cfg.in_fmt == SPX_FMT_CF32) ka_c<<<(unsigned)grid_a, C::THREADS_A, smem_a, st>>>(p);
-    else ka_i<<<(unsigned)grid_a, C::THREADS_A, smem_a, st>>>(p);
+    // kernel A: grid = column groups x frame lanes (a multiple of the group count: a CTA keeps its columns)
+    constexpr int GROUPS_A = N2 / C::G;
+    const int resident_a = pl->sm_count * occ_a[dev][cf32 ? 0 : 1];
+    int lanes = resident_a / GROUPS_A;
+    if (lanes < 1) lanes = 1;
+    if (lanes > p.frames) lanes = p.frames;
+    const unsigned grid_a = (unsigned)(GROUPS_A * lanes);
+    if (cf32) ka_c<<<grid_a, C::THREADS_A, smem_a, st>>>(p);
+    else ka_i<<<grid_a, C::THREADS_A, smem_a, st>>>(p);
     SPX_CUDA(cudaGetLastError());
-    // kernel B: (row groups) x (frame chunks) work items; chunk size balances SM fill vs atomic flushes
+    // kernel B: (row groups) x (frame chunks) work items, one resident wave; accumulators flush once per item
     const int groups = N1 / C::FPC;
-    const int want_items = pl->sm_count * 2;
-    int chunks = (want_items + groups - 1) / groups;
+    const int resident_b = pl->sm_count * occ_b[dev][acc ? 0 : 1];
+    int chunks = (resident_b + groups - 1) / groups;
     if (chunks > p.frames) chunks = p.frames;
     if (chunks < 1) chunks = 1;
     p.frames_per_chunk = (p.frames + chunks - 1) / chunks;
     const long long items_b = (long long)groups * ((p.frames + p.frames_per_chunk - 1) / p.frames_per_chunk);
-    long long grid_b = items_b < (long long)pl->sm_count * 4 ? items_b : (long long)pl->sm_count * 4;
+    const long long grid_b = items_b < resident_b ? items_b : resident_b;
     if (acc) kb_a<<<(unsigned)grid_b, C::THREADS_B, smem_b, st>>>(p);
     else kb_n<<<(unsigned)grid_b, C::THREADS_B, smem_b, st>>>(p);
     SPX_CUDA(cudaGetLastError());
@@ -352,6 +441,8 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
     p.db_pw_min = pl->cfg.db_eps * pl->cfg.db_eps * 1099511627776.0f;
     p.q_vmin = vmin;
     p.q_scale = 256.0f / (vmax - vmin);
+    p.q_a = (float)(3.01029995663981195214 * 256.0 / ((double)vmax - (double)vmin));
+    p.q_b = (float)(-(double)vmin * 256.0 / ((double)vmax - (double)vmin));
     p.sys_atomics = sys_atomics;
     for (long long f0 = 0; f0 < frames; f0 += fb) {
         p.frames = (int)(frames - f0 < fb ? frames - f0 : fb);

@@ -35,7 +35,7 @@ struct spx_plan {
     int big_n1 = 0, big_n2 = 0;
     float2* d_big_tw = nullptr;  // one allocation holding the four tables below
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_wn_fine = nullptr, *d_wn_coarse = nullptr;
-    size_t big_scratch_bytes = 96u << 20;  // frames per batch = scratch / (nfft * 8): sized to stay in the 126 MB L2
+    size_t big_scratch_bytes = 192u << 20;  // frames per batch = scratch / (nfft * 8); measured best on B200 (T round-trips through HBM either way)
     spx::DevBuf st_big;
     std::mutex mu;
 };
