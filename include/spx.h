@@ -41,7 +41,7 @@ extern "C" {
 #define SPX_E_INVALID (-1)     /* bad argument */
 #define SPX_E_CUDA (-2)        /* CUDA runtime / launch failure */
 #define SPX_E_NOMEM (-3)       /* allocation failed */
-#define SPX_E_UNSUPPORTED (-4) /* e.g. nfft not a power of two in [16, 1048576] */
+#define SPX_E_UNSUPPORTED (-4) /* e.g. nfft outside the supported range */
 #define SPX_E_NODEVICE (-5)    /* no CUDA device: there is NO CPU fallback */
 #define SPX_E_BUSY (-6)        /* ring full / nothing to collect */
 
@@ -106,7 +106,9 @@ typedef struct spx_plan spx_plan;
 typedef struct {
     uint32_t struct_size; /* sizeof(spx_plan_config) */
     int32_t device;
-    int32_t nfft;     /* power of two, 16 .. 1048576 */
+    int32_t nfft;     /* power of two in [16, 1048576] (shared-memory / four-step kernels), or any length in
+                       * [1, 524288] (Bluestein over the power-of-two kernels: the reference's np.fft.fft takes any
+                       * rx_buffer_size, streamer.py:8-10,119) */
     int32_t hop;      /* 1 .. nfft (nfft = no overlap, nfft/4 = 75 % overlap) */
     int32_t window;   /* SPX_WINDOW_* */
     int32_t in_fmt;   /* SPX_FMT_* */

@@ -68,6 +68,17 @@ int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long l
                        float* db_rows, unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold,
                        float vmin, float vmax, cudaStream_t st, int sys_atomics) {
     if (frames <= 0 || n_streams <= 0) return SPX_OK;
+    if (pl->blu_m) {  // arbitrary length: Bluestein over the inner power-of-two plan, one stream at a time
+        const size_t elt = pl->cfg.in_fmt == SPX_FMT_CI16 ? 4 : 8;
+        const size_t N = (size_t)pl->cfg.nfft;
+        for (long long s = 0; s < n_streams; ++s) {
+            const size_t r0 = (size_t)(s * frames);
+            SPX_TRY(bluestein_launch_stream(pl, (const char*)in + (size_t)(s * stream_stride) * elt, frames, (long long)r0,
+                                            db_rows, wf_rows, spec_rows, welch_acc ? welch_acc + s * N : nullptr,
+                                            maxhold ? maxhold + s * N : nullptr, vmin, vmax, st, sys_atomics));
+        }
+        return SPX_OK;
+    }
     if (pl->cfg.nfft >= 16384) {  // four-step path, one stream at a time
         const size_t elt = pl->cfg.in_fmt == SPX_FMT_CI16 ? 4 : 8;
         const size_t N = (size_t)pl->cfg.nfft;
@@ -437,8 +448,9 @@ int spx_plan_create(spx_plan** out, const spx_plan_config* cfg) {
     *out = nullptr;
     if (cfg->struct_size != sizeof(spx_plan_config))
         return spx_set_error(SPX_E_INVALID, "spx_plan_config.struct_size %u != %zu", cfg->struct_size, sizeof(spx_plan_config));
-    if (!is_pow2(cfg->nfft) || cfg->nfft < 16 || cfg->nfft > (1 << 20))
-        return spx_set_error(SPX_E_UNSUPPORTED, "nfft %d must be a power of two in [16, 1048576]", cfg->nfft);
+    const bool native_len = is_pow2(cfg->nfft) && cfg->nfft >= 16;
+    if (cfg->nfft < 1 || cfg->nfft > (1 << 20) || (!native_len && cfg->nfft > (1 << 19)))
+        return spx_set_error(SPX_E_UNSUPPORTED, "nfft %d: supported lengths are powers of two in [16, 1048576] and any length in [1, 524288]", cfg->nfft);
     if (cfg->hop < 1 || cfg->hop > cfg->nfft) return spx_set_error(SPX_E_INVALID, "hop %d must be in [1, nfft]", cfg->hop);
     if (cfg->window < 0 || cfg->window > 2) return spx_set_error(SPX_E_INVALID, "unknown window %d", cfg->window);
     if (cfg->in_fmt != SPX_FMT_CF32 && cfg->in_fmt != SPX_FMT_CI16) return spx_set_error(SPX_E_INVALID, "unknown in_fmt %d", cfg->in_fmt);
@@ -470,7 +482,9 @@ int spx_plan_create(spx_plan** out, const spx_plan_config* cfg) {
             if ((e = cudaMalloc(&pl->d_win, wf.size() * sizeof(float))) != cudaSuccess) { rc = spx_set_error(SPX_E_NOMEM, "%s", cudaGetErrorString(e)); break; }
             if ((e = cudaMemcpy(pl->d_win, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = spx_set_error(SPX_E_CUDA, "%s", cudaGetErrorString(e)); break; }
         }
-        if (cfg->nfft > 8192) {
+        if (!native_len) {
+            if ((rc = bluestein_plan_init(pl)) != SPX_OK) break;
+        } else if (cfg->nfft > 8192) {
             if ((rc = bigfft_plan_init(pl)) != SPX_OK) break;
         } else {
             std::vector<float2> tw = build_twiddles(cfg->nfft);
@@ -499,6 +513,8 @@ int spx_plan_destroy(spx_plan* pl) {
     if (pl->d_win) cudaFree(pl->d_win);
     if (pl->d_tw) cudaFree(pl->d_tw);
     if (pl->d_big_tw) cudaFree(pl->d_big_tw);
+    if (pl->d_blu) cudaFree(pl->d_blu);
+    if (pl->blu_inner) spx_plan_destroy(pl->blu_inner);
     pl->st_big.release();
     pl->st_in.release(); pl->st_db.release(); pl->st_wf.release(); pl->st_spec.release();
     pl->st_welch.release(); pl->st_max.release(); pl->st_misc.release(); pl->st_flush.release();

@@ -37,6 +37,10 @@ struct spx_plan {
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_wn_fine = nullptr, *d_wn_coarse = nullptr;
     size_t big_scratch_bytes = 192u << 20;  // frames per batch = scratch / (nfft * 8); measured best on B200 (T round-trips through HBM either way)
     spx::DevBuf st_big;
+    // Bluestein path (nfft not a power of two, or < 16): inner power-of-two plan of length blu_m
+    int blu_m = 0;
+    spx_plan* blu_inner = nullptr;
+    float2* d_blu = nullptr;  // [N] window*scale*chirp, [N] chirp/M, [M] FFT_M(conj chirp) in fftshift order
     std::mutex mu;
 };
 
@@ -49,4 +53,8 @@ int bigfft_plan_init(spx_plan* pl);
 int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
                          unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
                          float vmax, cudaStream_t st, int sys_atomics = 0);
+int bluestein_plan_init(spx_plan* pl);
+int bluestein_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
+                            unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
+                            float vmax, cudaStream_t st, int sys_atomics = 0);
 }  // namespace spx

@@ -144,7 +144,9 @@ def test_edge_cases(sp):
     r = pl.stft(np.zeros(1024, np.complex64), db_rows=True, wf_rows=True)  # exactly one all-zero frame
     assert r.n_frames == 1 and np.abs(r.db_rows + 240.0).max() < 1e-3 and np.all(r.wf_rows == 0)
     with pytest.raises(sp.SpectralError):
-        sp.SpectralPlan(1000)          # not a power of two
+        sp.SpectralPlan((1 << 19) + 2)  # beyond the supported non-power-of-two range
+    with pytest.raises(sp.SpectralError):
+        sp.SpectralPlan(0)
     with pytest.raises(sp.SpectralError):
         sp.SpectralPlan(1024, 2048)    # hop > nfft
     pl.close()
@@ -309,3 +311,40 @@ def test_peer_output_pipeline_matches_direct_outputs(sp, monkeypatch, nfft, hop,
         np.testing.assert_array_equal(tgt.buffers["maxhold"].array.to_host(), ref.maxhold)
     tgt.close()
     pl.close()
+
+
+@pytest.mark.parametrize("nfft,hop,kind,fmt", [(1000, 1000, "rect", 0), (1000, 250, "hann", 1), (4095, 2048, "hann", 0),
+                                               (4097, 4097, "blackman", 0), (7, 3, "rect", 0), (1, 1, "rect", 0),
+                                               (12, 12, "hann", 0), (3000, 1500, "hann", 1), (100000, 50000, "hann", 0)])
+def test_arbitrary_length_bluestein_parity(sp, nfft, hop, kind, fmt):
+    """Frame lengths that are not a power of two (the reference's np.fft.fft takes any rx_buffer_size): Bluestein over
+    the power-of-two kernels.  Same parity rules; fftshift follows numpy for odd N (out[j] = X[(j - N//2) mod N])."""
+    F = 9 if nfft < 50000 else 3
+    L = nfft + hop * (F - 1) + min(5, hop - 1)
+    x = sref.synth_iq(L, seed=nfft % 97 + 1)
+    x = sref.to_ci16(x) if fmt else x.astype(np.complex64)
+    pl = sp.SpectralPlan(nfft, hop, kind, fmt)
+    vmin, vmax = (20.0, 150.0) if fmt else (-40.0, 90.0)
+    r = pl.stft(x, db_rows=True, wf_rows=True, spectrum=True, welch=True, maxhold=True, vmin=vmin, vmax=vmax)
+    assert r.n_frames == F
+    X = oracle_rows(x, nfft, hop, kind, fmt=fmt)
+    P = X.real**2 + X.imag**2
+    assert np.all(np.abs(r.spectrum - X) <= 6e-6 * np.sqrt(P.mean()) + 2e-6 * np.abs(X) + 1e-7 * np.abs(X).max())
+    if nfft > 1:
+        parity.check_db_rows(r.db_rows, P, what=f"N={nfft}")
+        parity.check_power(r.welch_acc[0], P.sum(axis=0), what="welch")
+        parity.check_power(r.maxhold[0], P.max(axis=0), what="maxhold")
+        parity.check_u8(r.wf_rows, sref.amplitude_db(X), vmin, vmax, what="u8")
+    pl.close()
+
+
+def test_stream_frame_any_buffer_size(sp):
+    """The drop-in for streamer.py:119-121 with rx_buffer_size = 1000 and 3001 (odd): freqs and power_db as numpy gives them."""
+    rng = np.random.default_rng(4)
+    for n in (1000, 3001):
+        s = (rng.integers(-2047, 2048, n) + 1j * rng.integers(-2047, 2048, n)).astype(np.complex128)
+        f, p = sp.stream_frame(s, 1e6, 2.4e9)
+        f_ref, p_ref = sref.stream_frame(s, 1e6, 2.4e9)
+        assert np.array_equal(f, f_ref)
+        X = np.fft.fftshift(np.fft.fft(s))
+        parity.check_db_rows(p[None, :], (X.real**2 + X.imag**2)[None, :], what=f"stream N={n}")
