@@ -280,6 +280,24 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---------------- context for the roofline: measured FP32 peak, and the HBM-bound headline shape of north_star
+    # (cf32 in, hop = N, f32 dB rows: 12 B/sample, 80 nominal flop/sample) timed the same way on 61 440 000 samples
+    # (492 MB in + 246 MB out per launch: several times the 126 MB L2, so no explicit flush)
+    p32 = nat.fp32_peak_tflops(dev)
+    Lh = L_STEP
+    plh = sp.SpectralPlan(NFFT, NFFT, "hann", sp.FMT_CF32, device=dev)
+    rngh = np.random.default_rng(1)
+    d_xh = nat.DeviceArray.from_host(rngh.standard_normal(2 * Lh).astype(np.float32).view(np.complex64), dev)
+    d_dbh = nat.DeviceArray((Lh // NFFT, NFFT), np.float32, dev)
+    _, ms_h = plh.time_stft(d_xh, warmup=3, iters=10, flush_l2=False, db_rows=d_dbh)
+    ms_h = float(np.median(ms_h))
+    headline = {"shape": "cf32 in, 4096-pt Hann, hop = N, f32 dB rows (12 B/sample), 61 440 000 samples per launch (738 MB of traffic, "
+                         "larger than L2; no flush)",
+                "kernel_ms": round(ms_h, 4), "Msamples_per_s": round(Lh / (ms_h * 1e-3) / 1e6, 1),
+                "achieved_gbs": round(Lh * 12 / (ms_h * 1e-3) / 1e9, 1),
+                "frac_of_hbm_peak": round(Lh * 12 / (ms_h * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+    plh.close(); d_xh.free(); d_dbh.free()
+
     k_ms = float(np.mean(kernel_ms))
     achieved = L_STEP * BYTES_PER_SAMPLE / (k_ms * 1e-3) / 1e9
     traffic = None
@@ -310,7 +328,11 @@ def main():
                      "kernel": "stft_kernel<4096,ci16,acc>", "kernel_ms": round(k_ms, 4),
                      "bytes_per_sample": BYTES_PER_SAMPLE, "kernel_share_of_step": round(k_ms * args.steps / (dt_dev * 1e3), 3),
                      "fp32_tflops_nominal": round(L_STEP * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12, 2),
-                     "note": "shape is FP32-issue bound (SURVEY 8d): 320 nominal flop/sample vs 8 B/sample"},
+                     "fp32_peak_tflops_measured": round(p32, 2),
+                     "frac_of_fp32_peak_nominal_flops": round(L_STEP * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12 / p32, 4),
+                     "note": "this shape transforms every sample 4 times (75% overlap): 320 nominal flop/sample vs 8 B/sample, "
+                             "so FP32 issue binds before HBM (SURVEY 8d); the HBM-bound shape of north_star is in headline_shape",
+                     "headline_shape": headline},
         "clocks": clocks,
         "features": {"snr_db": round(feat["snr_db"], 2), "peak_count": feat["peak_count"]},
     }

@@ -75,6 +75,11 @@ SPX_API int spx_get_device_info(int device, spx_device_info* out);
  * (one rx buffer = one frame at streamer.py:114-119; mlab framing behind process_sigmf_data.py:188) */
 SPX_API int64_t spx_frame_count(int64_t n_samples, int32_t nfft, int32_t hop);
 
+/* Measured FP32 peak of the device: an FFMA micro-kernel (8 independent chains per thread, every SM full), best of
+ * 5 launches timed with CUDA events.  tflops_out = 2 * lane-FMAs / time.  bench.py reports the STFT kernel's FP32
+ * pipe share against it ("measure P32 with an FMA micro-kernel in the same run"). */
+SPX_API int spx_fp32_peak(int device, double* tflops_out);
+
 /* ---------------------------------------------------------------- pinned host memory */
 SPX_API int spx_host_alloc(void** out, size_t bytes);
 SPX_API int spx_host_free(void* p);

@@ -129,6 +129,7 @@ _SIGNATURES = {
     "spx_ring_stats": (C.c_int, [C.c_void_p, C.POINTER(spx_ring_stats_t)]),
     "spx_plan_window_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "spx_plan_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "spx_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "spx_ipc_export": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "spx_ipc_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "spx_ipc_close": (C.c_int, [C.c_int, C.c_void_p]),
@@ -212,6 +213,13 @@ def device_info(device: int = 0) -> dict:
     check(lib().spx_get_device_info(device, C.byref(info)))
     return {"name": info.name.decode(), "sm_count": info.sm_count, "cc": (info.cc_major, info.cc_minor),
             "l2_bytes": info.l2_bytes, "max_smem_optin": info.max_smem_optin, "total_mem": info.total_mem}
+
+
+def fp32_peak_tflops(device: int = 0) -> float:
+    """Measured FP32 FMA peak of the device (micro-kernel inside libspx), TFLOP/s."""
+    v = C.c_double()
+    check(lib().spx_fp32_peak(device, C.byref(v)))
+    return float(v.value)
 
 
 def frame_count(n_samples: int, nfft: int, hop: int) -> int:

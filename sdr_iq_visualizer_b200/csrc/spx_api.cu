@@ -316,6 +316,20 @@ static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cu
     return SPX_OK;
 }
 
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters, float a, float b) {
+    float r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = threadIdx.x * 1e-3f + (float)i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void welch_finalize_kernel(const double* __restrict__ acc, int n, double inv_norm, double* pxx, double* pxx_db) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -529,6 +543,36 @@ int spx_plan_sync(spx_plan* pl) {
     SPX_CUDA(cudaStreamSynchronize(pl->s_h2d));
     SPX_CUDA(cudaStreamSynchronize(pl->s_compute));
     SPX_CUDA(cudaStreamSynchronize(pl->s_d2h));
+    return SPX_OK;
+}
+
+int spx_fp32_peak(int device, double* tflops_out) {
+    if (!tflops_out) return spx_set_error(SPX_E_INVALID, "tflops_out is NULL");
+    SPX_CUDA(cudaSetDevice(device));
+    int sm = 0;
+    SPX_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sm * 8, iters = 1 << 13;
+    float* out = nullptr;
+    SPX_CUDA(cudaMalloc(&out, sizeof(float) * (size_t)blocks * 256));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int k = 0; k < 6; ++k) {
+        cudaEventRecord(e0, 0);
+        fp32_probe_kernel<<<blocks, 256>>>(out, iters, 1.0001f, 0.5f);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (k > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(out);
+    if (e != cudaSuccess) return spx_set_error(SPX_E_CUDA, "fp32 probe: %s", cudaGetErrorString(e));
+    *tflops_out = 2.0 * (double)blocks * 256.0 * (double)iters * 16.0 / ((double)best * 1e-3) / 1e12;
     return SPX_OK;
 }
 

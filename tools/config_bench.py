@@ -1,0 +1,101 @@
+#!/usr/bin/env python3
+"""Single-GPU measurements of the BASELINE configs that are not the bench line: C1 (SigMF file ->
+PSD + waterfall), C3 (16 Mi samples -> frame stats + 256x256 I/Q histogram), plus the classifier-feature kernel on a
+batch of spectra.  Device-resident numbers use CUDA events on the launching stream; end-to-end numbers are host
+buffers through the public API.  One JSON line per case."""
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sdr_iq_visualizer_b200 import _native as nat, features, sigmf_io, spectral as sp, synth, timedomain as td  # noqa: E402
+
+HBM = 6539.9
+try:
+    HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timed(fn, stream=0, warmup=3, iters=10):
+    t = nat.DeviceTimer(0, stream)
+    for _ in range(warmup):
+        fn()
+    ms = []
+    for _ in range(iters):
+        t.start(); fn(); t.stop()
+        ms.append(t.elapsed_ms())
+    return float(np.median(ms)), float(min(ms))
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def c1():
+    L, n, hop = 1 << 20, 1024, 512
+    x = synth.synth_iq(L, seed=1).astype(np.complex64)
+    with tempfile.TemporaryDirectory() as d:
+        base = sigmf_io.write_recording(os.path.join(d, "c1"), x, 1e6, 2.4e9)
+        for _ in range(2):
+            sigmf_io.process_recording(base, n, hop, "hann", waterfall=True, vmin=-60.0, vmax=70.0)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            out = sigmf_io.process_recording(base, n, hop, "hann", waterfall=True, vmin=-60.0, vmax=70.0)
+            ts.append(time.perf_counter() - t0)
+    pl = sp.SpectralPlan(n, hop, "hann", sp.FMT_CF32)
+    dx = nat.DeviceArray.from_host(x)
+    F = pl.frame_count(L)
+    kw = dict(wf_rows=nat.DeviceArray((F, n), np.uint8), welch=nat.DeviceArray((1, n), np.float64), maxhold=nat.DeviceArray((1, n), np.float32))
+    _, ms = pl.time_stft(dx, warmup=3, iters=10, vmin=-60.0, vmax=70.0, **kw)
+    emit(case="C1 SigMF cf32 2^20 samples, 1024-pt Hann 50%: file -> PSD + u8 waterfall", e2e_ms=round(min(ts) * 1e3, 3),
+         e2e_Msps=round(L / min(ts) / 1e6, 1), kernel_us=round(float(np.median(ms)) * 1e3, 2),
+         kernel_GSps=round(L / (float(np.median(ms)) * 1e-3) / 1e9, 1), frames=out.n_frames,
+         note="8 MiB of input: launch/latency bound on a B200; CPU/oracle config of BASELINE")
+
+
+def c3():
+    L = 1 << 24
+    rng = np.random.default_rng(3)
+    xc = (0.7 * (rng.standard_normal(L) + 1j * rng.standard_normal(L))).astype(np.complex64)
+    xi = synth.to_ci16(xc.astype(np.complex128) * (1.0 / 0.7))
+    for name, x, fmt, r, bps in (("cf32", xc, sp.FMT_CF32, 4.0, 8), ("ci16", xi, sp.FMT_CI16, 2048.0, 4)):
+        dx = nat.DeviceArray.from_host(x)
+        dh = nat.DeviceArray((256, 256), np.uint32, zero=True)
+        med, best = timed(lambda: td.iq_hist2d(dx, r, 256, in_fmt=fmt, out=dh))
+        emit(case=f"C3 I/Q 256x256 histogram, 2^24 {name} samples (device-resident)", kernel_us=round(med * 1e3, 2),
+             GSps=round(L / (med * 1e-3) / 1e9, 1), hbm_frac=round(L * bps / (med * 1e-3) / 1e9 / HBM, 3), bytes_per_sample=bps)
+        med, best = timed(lambda: td.frame_stats(dx, 4096, 4096, in_fmt=fmt))
+        emit(case=f"C3 per-frame mean/peak power, 4096-sample frames, 2^24 {name} samples (device-resident, incl. output allocs)",
+             kernel_us=round(med * 1e3, 2), GSps=round(L / (med * 1e-3) / 1e9, 1),
+             hbm_frac=round(L * bps / (med * 1e-3) / 1e9 / HBM, 3), bytes_per_sample=bps)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            td.iq_hist2d(x, r, 256, in_fmt=fmt)
+        dt = (time.perf_counter() - t0) / 3
+        emit(case=f"C3 histogram end to end from pageable host memory ({name})", e2e_ms=round(dt * 1e3, 2), e2e_GSps=round(L / dt / 1e9, 2))
+        dx.free()
+
+
+def k3():
+    rng = np.random.default_rng(4)
+    for n, batch in ((4096, 1), (4096, 64), (4096, 1024), (65536, 64)):
+        p = rng.normal(-80, 3, (batch, n))
+        dp = nat.DeviceArray.from_host(p)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            features.measure_batch(dp, n=n, batch=batch, want_peaks=False)
+        dt = (time.perf_counter() - t0) / 5
+        emit(case=f"K3 classifier features, {batch} spectra x {n} bins (float64, device-resident, host round trip included)",
+             ms=round(dt * 1e3, 3), spectra_per_s=round(batch / dt, 1))
+        dp.free()
+
+
+if __name__ == "__main__":
+    print(json.dumps(nat.device_info(0)))
+    c1(); c3(); k3()
