@@ -200,6 +200,14 @@ def main():
         return
 
     rank, world, local, dist = dist_setup(args.gpus)
+    try:  # keep this rank's pinned buffers and threads on the NUMA node its GPU hangs off
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis else local
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
     from sdr_iq_visualizer_b200 import _native as nat
     from sdr_iq_visualizer_b200 import features, spectral as sp
     nat.require_device()

@@ -176,8 +176,16 @@ static int stft_exec_host(spx_plan* pl, spx_stft_args* a, long long F) {
         const char* h_in = (const char*)a->in + (size_t)(s * stride_host) * elt;
         char* dd = d_in + (size_t)(s * L) * elt;
         long long f_lo = 0;
-        for (long long lo = 0; lo < L; lo += piece) {
-            const long long hi = lo + piece < L ? lo + piece : L;
+        // piece schedule: ramp up from piece/8 and back down at the end, so that the un-overlapped head (first H2D
+        // before any kernel) and tail (last D2H after the last kernel) of the three-stream pipeline stay short
+        long long step = 0;
+        int k = 0;
+        for (long long lo = 0; lo < L; lo += step, ++k) {
+            const long long left = L - lo;
+            step = piece >> (k < 3 ? 3 - k : 0);
+            if (left <= piece) step = left > piece / 4 ? (left + 1) / 2 : left;
+            if (step < (long long)N) step = (long long)N;
+            const long long hi = lo + step < L ? lo + step : L;
             SPX_CUDA(cudaMemcpyAsync(dd + (size_t)lo * elt, h_in + (size_t)lo * elt, (size_t)(hi - lo) * elt,
                                      cudaMemcpyHostToDevice, pl->s_h2d));
             h2d += (hi - lo) * (long long)elt;
@@ -271,8 +279,17 @@ static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cu
     long long piece = (long long)(pl->peer_piece_bytes / (size_t)N);
     if (piece < 1) piece = 1;
     if (piece > F) piece = F;
-    unsigned char* stage[2] = {nullptr, nullptr};
+    // rows that live on THIS GPU (the owner's own shard) are written by the kernel directly: no staging, no copy
+    bool rows_local = false;
     if (a->wf_rows) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, a->wf_rows) == cudaSuccess)
+            rows_local = at.type == cudaMemoryTypeDevice && at.device == pl->cfg.device;
+        else
+            cudaGetLastError();
+    }
+    unsigned char* stage[2] = {nullptr, nullptr};
+    if (a->wf_rows && !rows_local) {
         SPX_TRY(pl->st_wf.reserve((size_t)(2 * piece) * N));
         stage[0] = (unsigned char*)pl->st_wf.ptr;
         stage[1] = stage[0] + (size_t)piece * N;
@@ -290,11 +307,13 @@ static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cu
         for (long long f_lo = 0; f_lo < F; f_lo += piece, ++idx) {
             const long long nf = F - f_lo < piece ? F - f_lo : piece;
             const int b = (int)(idx & 1);
-            if (idx >= 2 && a->wf_rows) SPX_CUDA(cudaStreamWaitEvent(st, e_c[b], 0));   // the copy that last used this buffer is done
-            SPX_TRY(stft_launch_device(pl, in_s + (size_t)(f_lo * hop) * elt, 1, 0, nf, nullptr, stage[b], nullptr,
+            const bool staged = a->wf_rows && !rows_local;
+            if (idx >= 2 && staged) SPX_CUDA(cudaStreamWaitEvent(st, e_c[b], 0));   // the copy that last used this buffer is done
+            unsigned char* rows_dst = staged ? stage[b] : (a->wf_rows ? a->wf_rows + (size_t)(s * F + f_lo) * N : nullptr);
+            SPX_TRY(stft_launch_device(pl, in_s + (size_t)(f_lo * hop) * elt, 1, 0, nf, nullptr, rows_dst, nullptr,
                                        w_local ? w_local + s * N : nullptr, m_local ? m_local + s * N : nullptr,
                                        a->vmin, a->vmax, st, 0));
-            if (!a->wf_rows) continue;
+            if (!staged) continue;
             SPX_CUDA(cudaEventRecord(e_k[b], st));
             SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, e_k[b], 0));
             SPX_CUDA(cudaMemcpyAsync(a->wf_rows + (size_t)(s * F + f_lo) * N, stage[b], (size_t)nf * N, cudaMemcpyDefault, pl->s_d2h));
@@ -308,7 +327,7 @@ static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cu
         SPX_CUDA(cudaGetLastError());
     }
     // whoever waits on `st` (spx_plan_sync, a later launch) also waits for the last copies
-    if (a->wf_rows) {
+    if (a->wf_rows && !rows_local) {
         SPX_CUDA(cudaStreamWaitEvent(st, e_c[0], 0));
         if (idx >= 2) SPX_CUDA(cudaStreamWaitEvent(st, e_c[1], 0));
     }
