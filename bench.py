@@ -239,10 +239,13 @@ def main():
         if ktimer is not None:
             ktimer.stop()
         pl.welch_finalize(d_we, res.n_frames, FS, pxx=d_pxx, pdb=d_pdb)
-        return features.measure_batch(d_pdb, n=NFFT, batch=1, device=dev, stream=st)[0]
+        # classifier features of this Welch block: kernel + asynchronous copy of the result struct to pinned memory,
+        # everything enqueued on the plan's stream (the host never waits inside a step; results are read after the loop)
+        return fq.enqueue(d_pdb, NFFT)
 
+    fq = features.FeatureQueue(1, dev, st, slots=max(args.steps, args.warmup, 1))
     for _ in range(args.warmup):
-        feat = device_step(None)
+        device_step(None)
     sampler = ClockSampler(dev)
     if dist is not None:
         dist.barrier()
@@ -250,10 +253,11 @@ def main():
     sampler.start()
     total_timer.start()
     for i in range(args.steps):
-        feat = device_step(kernel_timers[i])
+        last_slot = device_step(kernel_timers[i])
     total_timer.stop()
     dt_dev = total_timer.elapsed_ms() * 1e-3
     nat.device_sync(dev)
+    feat = fq.results(last_slot)[0]
     kernel_ms = [t.elapsed_ms() for t in kernel_timers]
     dt_dev = barrier_max(dist, local, dt_dev)
 

@@ -92,6 +92,7 @@ SPX_API int spx_device_alloc(int device, void** out, size_t bytes);
 SPX_API int spx_device_free(int device, void* p);
 SPX_API int spx_memcpy_h2d(int device, void* dst, const void* src, size_t bytes);
 SPX_API int spx_memcpy_d2h(int device, void* dst, const void* src, size_t bytes);
+SPX_API int spx_memcpy_d2h_async(int device, void* dst_host, const void* src, size_t bytes, void* stream);
 SPX_API int spx_memset(int device, void* dst, int value, size_t bytes);
 SPX_API int spx_device_sync(int device);
 
@@ -147,9 +148,11 @@ typedef struct {
     int64_t n_frames_out; /* out: F */
     int64_t h2d_bytes_out;/* out: bytes copied host->device by this call (SPX_MEM_HOST) */
     int64_t d2h_bytes_out;/* out: bytes copied device->host by this call */
-    int32_t peer_outputs; /* SPX_MEM_DEVICE only: 1 = welch_acc / maxhold / rows may live on ANOTHER GPU (mapped with
-                           * spx_ipc_open); the accumulator flushes then use system-scope atomics so that several GPUs
-                           * can reduce into one buffer over NVLink inside the STFT kernel itself */
+    int32_t peer_outputs; /* SPX_MEM_DEVICE only, bit mask.  bit 0: welch_acc / maxhold are shared with other GPUs (this
+                           * GPU's or a peer's memory mapped with spx_ipc_open): partials are reduced locally and added
+                           * with system-scope atomics, so several GPUs reduce into one buffer over NVLink.  bit 1:
+                           * wf_rows lives on a peer GPU: rows are staged in frame pieces and pushed by the copy engine
+                           * while the next piece is transformed */
     int32_t reserved;
 } spx_stft_args;
 
@@ -230,6 +233,13 @@ typedef struct {
 SPX_API int spx_classify_features(int32_t device, int32_t mem, const void* power_db, int32_t dtype, int32_t n,
                                   int32_t batch, int64_t stride, spx_features* out, int32_t* peaks,
                                   int32_t peaks_cap, const spx_feature_opts* opts, void* stream);
+
+/* Enqueue-only variant for pipelines that must not stall the host: device input, device output (`out_dev[batch]`,
+ * optional `peaks_dev[batch][peaks_cap]`), nothing is copied or synchronised.  Pair it with spx_memcpy_d2h_async
+ * into pinned memory and read the results after the stream has been synchronised. */
+SPX_API int spx_classify_features_dev(int32_t device, const void* power_db_dev, int32_t dtype, int32_t n, int32_t batch,
+                                      int64_t stride, spx_features* out_dev, int32_t* peaks_dev, int32_t peaks_cap,
+                                      const spx_feature_opts* opts, void* stream);
 
 /* ---------------------------------------------------------------- time-domain / constellation views */
 /* 2-D I/Q density histogram with np.histogram2d(I, Q, bins, range=[[-R,R],[-R,R]]) semantics

@@ -101,6 +101,7 @@ _SIGNATURES = {
     "spx_device_free": (C.c_int, [C.c_int, C.c_void_p]),
     "spx_memcpy_h2d": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "spx_memcpy_d2h": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "spx_memcpy_d2h_async": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "spx_memset": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_size_t]),
     "spx_device_sync": (C.c_int, [C.c_int]),
     "spx_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(spx_plan_config)]),
@@ -116,6 +117,8 @@ _SIGNATURES = {
     "spx_classify_features": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                         C.POINTER(spx_features), C.c_void_p, C.c_int32, C.POINTER(spx_feature_opts),
                                         C.c_void_p]),
+    "spx_classify_features_dev": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                            C.c_void_p, C.c_int32, C.POINTER(spx_feature_opts), C.c_void_p]),
     "spx_iq_hist2d": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_int64, C.c_double,
                                 C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "spx_frame_stats": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int64, C.c_int32,

@@ -279,15 +279,9 @@ static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cu
     long long piece = (long long)(pl->peer_piece_bytes / (size_t)N);
     if (piece < 1) piece = 1;
     if (piece > F) piece = F;
-    // rows that live on THIS GPU (the owner's own shard) are written by the kernel directly: no staging, no copy
-    bool rows_local = false;
-    if (a->wf_rows) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, a->wf_rows) == cudaSuccess)
-            rows_local = at.type == cudaMemoryTypeDevice && at.device == pl->cfg.device;
-        else
-            cudaGetLastError();
-    }
+    // rows that live on THIS GPU (the owner's own shard, peer_outputs bit 1 clear) are written by the kernel
+    // directly: no staging, no copy
+    const bool rows_local = (a->peer_outputs & 2) == 0;
     unsigned char* stage[2] = {nullptr, nullptr};
     if (a->wf_rows && !rows_local) {
         SPX_TRY(pl->st_wf.reserve((size_t)(2 * piece) * N));
@@ -439,6 +433,11 @@ int spx_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) {
 int spx_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
     SPX_CUDA(cudaSetDevice(device));
     SPX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SPX_OK;
+}
+int spx_memcpy_d2h_async(int device, void* dst_host, const void* src, size_t bytes, void* stream) {
+    SPX_CUDA(cudaSetDevice(device));
+    SPX_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return SPX_OK;
 }
 int spx_memset(int device, void* dst, int value, size_t bytes) {

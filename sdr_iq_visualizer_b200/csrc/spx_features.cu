@@ -363,3 +363,25 @@ extern "C" int spx_classify_features(int32_t device, int32_t mem, const void* po
     SPX_CUDA(cudaStreamSynchronize(st));
     return SPX_OK;
 }
+
+extern "C" int spx_classify_features_dev(int32_t device, const void* power_db_dev, int32_t dtype, int32_t n, int32_t batch,
+                                         int64_t stride, spx_features* out_dev, int32_t* peaks_dev, int32_t peaks_cap,
+                                         const spx_feature_opts* user_opts, void* stream) {
+    if (!out_dev || !power_db_dev) return spx_set_error(SPX_E_INVALID, "NULL argument");
+    if (batch < 1 || n < 1) return spx_set_error(SPX_E_INVALID, "batch and n must be positive");
+    if (dtype != 0 && dtype != 1) return spx_set_error(SPX_E_INVALID, "dtype must be 0 (float32) or 1 (float64)");
+    if (batch > 1 && stride < n) return spx_set_error(SPX_E_INVALID, "stride < n");
+    spx_feature_opts opts;
+    memset(&opts, 0, sizeof(opts));
+    opts.drop_db[0] = 3.0; opts.drop_db[1] = 10.0; opts.drop_db[2] = 20.0;
+    if (user_opts) opts = *user_opts;
+    if (peaks_dev && peaks_cap < 1) peaks_dev = nullptr;
+    SPX_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype)
+        features_kernel<double><<<batch, FT, 0, st>>>((const double*)power_db_dev, n, stride, out_dev, peaks_dev, peaks_cap, opts);
+    else
+        features_kernel<float><<<batch, FT, 0, st>>>((const float*)power_db_dev, n, stride, out_dev, peaks_dev, peaks_cap, opts);
+    SPX_CUDA(cudaGetLastError());
+    return SPX_OK;
+}

@@ -185,6 +185,8 @@ def fused_capture_step(plan, d_in, shard: CaptureShard, target: PeerReduceTarget
     if F_local <= 0:
         return 0
     rows = target.rows.rows(shard.f0, shard.f1) if target.rows is not None else False
+    # the owner writes its own rows directly; every other rank stages them and lets the copy engine push them
+    mode = 1 if target.rank == target.dst else 3
     plan.stft(d_in, wf_rows=rows, welch=target.welch, maxhold=target.maxhold, vmin=vmin, vmax=vmax, accumulate=True,
-              n_samples=shard.n_samples, peer_outputs=True)
+              n_samples=shard.n_samples, peer_outputs=mode)
     return F_local

@@ -73,3 +73,39 @@ def measure_batch(power_db, n: Optional[int] = None, batch: Optional[int] = None
 
 def measure(power_db, device: int = 0, **opts) -> dict:
     return measure_batch(power_db, device=device, **opts)[0]
+
+
+class FeatureQueue:
+    """Enqueue-only feature measurement for pipelines that must not stall the host (one Welch block after the
+    other on one stream): ``enqueue`` launches the kernel on device data and an asynchronous copy of the result
+    structs into pinned memory; ``results`` is read after the stream has been synchronised."""
+
+    def __init__(self, batch: int = 1, device: int = 0, stream: int = 0, slots: int = 1):
+        nat.require_device()
+        self.batch, self.device, self.stream, self.slots = int(batch), int(device), stream or None, int(slots)
+        self._sz = C.sizeof(nat.spx_features) * self.batch
+        self._dev = nat.DeviceArray((self.slots * self._sz,), np.uint8, device)
+        self._host = nat.pinned_empty(self.slots * self._sz, np.uint8)
+        self._opts = nat.spx_feature_opts()
+        self._opts.drop_db[0], self._opts.drop_db[1], self._opts.drop_db[2] = 3.0, 10.0, 20.0
+        self._next = 0
+
+    def enqueue(self, power_db, n: int, stride: Optional[int] = None, dtype=np.float64) -> int:
+        """Measure ``batch`` device-resident spectra of ``n`` bins; returns the slot the results will land in."""
+        slot = self._next % self.slots
+        self._next += 1
+        ptr, mem = nat.as_ptr(power_db)
+        if mem != nat.MEM_DEVICE:
+            raise ValueError("FeatureQueue needs device-resident spectra")
+        d_out = self._dev.ptr + slot * self._sz
+        nat.check(nat.lib().spx_classify_features_dev(self.device, ptr, 0 if np.dtype(dtype) == np.float32 else 1, int(n),
+                                                      self.batch, int(stride or n), d_out, None, 0, C.byref(self._opts),
+                                                      self.stream))
+        nat.check(nat.lib().spx_memcpy_d2h_async(self.device, self._host.ctypes.data + slot * self._sz, d_out, self._sz,
+                                                 self.stream))
+        return slot
+
+    def results(self, slot: int = 0) -> List[dict]:
+        """Feature dicts of a slot (call after synchronising the stream the work was enqueued on)."""
+        arr = (nat.spx_features * self.batch).from_buffer_copy(bytes(self._host[slot * self._sz:(slot + 1) * self._sz]))
+        return [_to_dict(arr[b], None) for b in range(self.batch)]

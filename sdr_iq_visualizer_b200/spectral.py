@@ -144,7 +144,7 @@ class SpectralPlan:
     # -- execution
     def stft(self, x, *, n_streams: int = 1, db_rows=False, wf_rows=False, spectrum=False, welch=False,
              maxhold=False, vmin: float = -100.0, vmax: float = 0.0, accumulate: bool = False,
-             stream: int = 0, n_samples: Optional[int] = None, peer_outputs: bool = False, _time=None) -> StftResult:
+             stream: int = 0, n_samples: Optional[int] = None, peer_outputs: int = 0, _time=None) -> StftResult:
         """Windowed STFT of ``x`` (1 stream, or ``n_streams`` equal-length streams laid out back to
         back).  Each output flag is False (not wanted), True (allocate) or a caller buffer to fill
         (numpy for host input, DeviceArray / CUDA tensor for device input)."""
@@ -186,7 +186,7 @@ class SpectralPlan:
         a.maxhold = nat.as_ptr(o_mh)[0]
         a.vmin, a.vmax = float(vmin), float(vmax)
         a.stream = stream or None
-        a.peer_outputs = 1 if peer_outputs else 0
+        a.peer_outputs = int(peer_outputs)   # bit 0: shared accumulators, bit 1: rows on a peer GPU (see spx.h)
         if _time is not None:
             warmup, iters, flush = _time
             ms = (C.c_float * iters)()

@@ -127,3 +127,22 @@ def test_float32_and_batch(clf):
     got_d = features.measure_batch(d)
     assert [g["peaks"] for g in got_d] == [g["peaks"] for g in got]
     assert [g["noise_floor_db"] for g in got_d] == [g["noise_floor_db"] for g in got]
+
+
+def test_feature_queue_matches_synchronous_call(clf):
+    """Enqueue-only measurement (device spectra -> pinned result structs, no host sync inside) == measure_batch."""
+    from sdr_iq_visualizer_b200 import _native as nat, features
+    rng = np.random.default_rng(12)
+    p = rng.normal(-80, 3, (5, 4096))
+    p[:, 1000] += 40
+    want = features.measure_batch(p, want_peaks=False)
+    dp = nat.DeviceArray.from_host(p)
+    fq = features.FeatureQueue(batch=5, slots=3)
+    slots = [fq.enqueue(dp, 4096) for _ in range(4)]          # wraps around the slot ring
+    nat.device_sync(0)
+    assert slots == [0, 1, 2, 0]
+    for s in (0, 1, 2):
+        got = fq.results(s)
+        for g, w in zip(got, want):
+            for k in ("noise_floor_db", "snr_db", "first_20db", "last_20db", "flatness", "kurtosis", "peak_count", "argmax"):
+                assert g[k] == w[k], k

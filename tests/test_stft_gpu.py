@@ -300,15 +300,21 @@ def test_peer_output_pipeline_matches_direct_outputs(sp, monkeypatch, nfft, hop,
     sh = sd.capture_shard(L, nfft, hop, 0, 1)
     assert (sh.f0, sh.f1) == (0, F)
     tgt = sd.PeerReduceTarget(nfft, F, 0, 1, 0)
-    for _ in range(2):                                                     # second pass reuses staging buffers and events
+    for mode in (3, 3, 1):                                                 # staged + copy engine (twice: buffers and events are reused), then direct rows
         tgt.zero()
-        assert sd.fused_capture_step(pl, d_in, sh, tgt, -20.0, 130.0) == F
+        nat.check(nat.lib().spx_memset(0, tgt.rows.ptr, 0, F * nfft))
+        pl.stft(d_in, wf_rows=tgt.rows.rows(0, F), welch=tgt.welch, maxhold=tgt.maxhold, vmin=-20.0, vmax=130.0, accumulate=True,
+                n_samples=L, peer_outputs=mode)
         pl.sync()
         rows = np.empty((F, nfft), np.uint8)
         nat.check(nat.lib().spx_memcpy_d2h(0, rows.ctypes.data, tgt.rows.ptr, rows.nbytes))
         np.testing.assert_array_equal(rows, ref.wf_rows)
         np.testing.assert_allclose(tgt.buffers["welch"].array.to_host(), ref.welch_acc, rtol=1e-6)  # fp32 partials regroup with the pieces
         np.testing.assert_array_equal(tgt.buffers["maxhold"].array.to_host(), ref.maxhold)
+    tgt.zero()
+    assert sd.fused_capture_step(pl, d_in, sh, tgt, -20.0, 130.0) == F      # the driver the sharded bench uses (owner: mode 1)
+    pl.sync()
+    np.testing.assert_allclose(tgt.buffers["welch"].array.to_host(), ref.welch_acc, rtol=1e-6)
     tgt.close()
     pl.close()
 
