@@ -181,30 +181,48 @@ def main():
         d_we = nat.DeviceArray((max(ns, 1), N), np.float64, dev)
         d_pdb = nat.DeviceArray((max(ns, 1), N), np.float64, dev)
         d_pxx = nat.DeviceArray((max(ns, 1), N), np.float64, dev)
+        import ctypes as C
         feats = [None]
+        FS_BYTES = C.sizeof(nat.spx_features)
+        per = -(-S // world)                      # streams per rank, padded so that every rank contributes the same size
+        t_mine = torch.zeros((per * FS_BYTES,), dtype=torch.uint8, device=f"cuda:{local}")
+        t_all = torch.zeros((world * per * FS_BYTES,), dtype=torch.uint8, device=f"cuda:{local}")
+        opts = nat.spx_feature_opts()
+        opts.drop_db[0], opts.drop_db[1], opts.drop_db[2] = 3.0, 10.0, 20.0
+
+        ext = torch.cuda.ExternalStream(pl.stream, device=torch.device("cuda", local))   # the plan's compute stream, seen by torch
+        ev_feat, ev_gather = torch.cuda.Event(), torch.cuda.Event()
+        state = {"gathered": False}
 
         def step():
-            barrier()
+            # independent streams: no barrier and no host wait inside the step; the only exchange is the all-gather of
+            # the feature structs (device to device over NCCL, a few KiB), ordered against the kernels with events
             if ns:
                 pl.stft(d_in, n_streams=ns, welch=d_we, n_samples=Ls)
                 pl.welch_finalize(d_we, F, 61.44e6, pxx=d_pxx, pdb=d_pdb, n_streams=ns)
-                mine = features.measure_batch(d_pdb, n=N, batch=ns, device=dev, stream=pl.stream, want_peaks=False)
-            else:
-                mine = []
-            # per-stream features (SNR, 3/10/20 dB occupied-bandwidth bins, flatness, kurtosis, peak count) -> every rank
-            packed = torch.tensor([[m["snr_db"], m["last_3db"] - m["first_3db"], m["last_10db"] - m["first_10db"],
-                                    m["last_20db"] - m["first_20db"], m["flatness"], m["kurtosis"], m["peak_count"]] for m in mine],
-                                  dtype=torch.float64, device=f"cuda:{local}").reshape(-1, 7)
+                if state["gathered"]:
+                    ext.wait_event(ev_gather)      # the previous all-gather has finished reading t_mine
+                nat.check(lib.spx_classify_features_dev(dev, d_pdb.ptr, 1, N, ns, N, int(t_mine.data_ptr()), None, 0,
+                                                        C.byref(opts), pl.stream))
+            ev_feat.record(ext)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev_feat)
             if world > 1:
-                per = -(-S // world)
-                pad = torch.zeros((per, 7), dtype=torch.float64, device=f"cuda:{local}")
-                pad[: packed.shape[0]] = packed
-                allf = torch.empty((world * per, 7), dtype=torch.float64, device=f"cuda:{local}")
-                dist.all_gather_into_tensor(allf, pad)
-                feats[0] = [allf[r * per: r * per + (sd.stream_block(S, r, world)[1] - sd.stream_block(S, r, world)[0])] for r in range(world)]
+                dist.all_gather_into_tensor(t_all, t_mine)
             else:
-                feats[0] = [packed]
-            barrier()
+                t_all.copy_(t_mine)
+            ev_gather.record(cur)
+            state["gathered"] = True
+
+        def parse():
+            raw = t_all.cpu().numpy().tobytes()
+            res = []
+            for r in range(world):
+                a, b = sd.stream_block(S, r, world)
+                arr = (nat.spx_features * (b - a)).from_buffer_copy(raw[r * per * FS_BYTES:(r * per + (b - a)) * FS_BYTES])
+                res.append([(f.snr_db, f.last_3db - f.first_3db, f.last_10db - f.first_10db, f.last_20db - f.first_20db,
+                             f.flatness, f.kurtosis, f.peak_count) for f in arr])
+            return res
 
         for _ in range(args.warmup):
             step()
@@ -218,7 +236,7 @@ def main():
                     "value": round(S * Ls * args.steps / dt / 1e6, 1), "ms_per_step": round(dt / args.steps * 1e3, 3),
                     "workload": f"config4: {S} streams x 2^{int(np.log2(Ls))} cf32, 2048-pt Hann, 50% overlap, per-stream Welch PSD "
                                 f"+ classifier features; streams {s0}..{s1 - 1} on rank {rank}",
-                    "features_gathered": sum(len(f) for f in feats[0])})
+                    "features_gathered": sum(len(f) for f in parse())})
         if args.check and rank == 0 and ns:
             from oracle import classifier_ref as cref, spectral_ref as sref
             from tests import parity
