@@ -82,6 +82,9 @@ SPX_API int spx_fp32_peak(int device, double* tflops_out);
 
 /* ---------------------------------------------------------------- pinned host memory */
 SPX_API int spx_host_alloc(void** out, size_t bytes);
+/* write-combined pinned memory: for buffers the CPU only WRITES sequentially and the GPU reads over PCIe (ring slots,
+ * staged input); CPU reads from it are slow.  Free with spx_host_free. */
+SPX_API int spx_host_alloc_wc(void** out, size_t bytes);
 SPX_API int spx_host_free(void* p);
 SPX_API int spx_host_register(void* p, size_t bytes);
 SPX_API int spx_host_unregister(void* p);

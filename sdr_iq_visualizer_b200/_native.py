@@ -94,6 +94,7 @@ _SIGNATURES = {
     "spx_get_device_info": (C.c_int, [C.c_int, C.POINTER(spx_device_info)]),
     "spx_frame_count": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "spx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "spx_host_alloc_wc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "spx_host_free": (C.c_int, [C.c_void_p]),
     "spx_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "spx_host_unregister": (C.c_int, [C.c_void_p]),
@@ -233,9 +234,9 @@ def frame_count(n_samples: int, nfft: int, hop: int) -> int:
 class _Pinned:
     """Owner of one cudaHostAlloc block, exposed to numpy through __array_interface__."""
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, write_combined: bool = False):
         p = C.c_void_p()
-        check(lib().spx_host_alloc(C.byref(p), nbytes))
+        check((lib().spx_host_alloc_wc if write_combined else lib().spx_host_alloc)(C.byref(p), nbytes))
         self.ptr = p.value
         self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
 
@@ -248,14 +249,15 @@ class _Pinned:
             pass
 
 
-def pinned_empty(shape, dtype) -> np.ndarray:
+def pinned_empty(shape, dtype, write_combined: bool = False) -> np.ndarray:
     """numpy array backed by page-locked host memory (cudaHostAlloc): makes the H2D/D2H legs of
-    SPX_MEM_HOST execution truly asynchronous.  The block is freed when the last view dies."""
+    SPX_MEM_HOST execution truly asynchronous.  The block is freed when the last view dies.
+    ``write_combined``: for input buffers the CPU only fills sequentially (never reads back)."""
     dtype = np.dtype(dtype)
     shape = tuple(int(v) for v in (shape if np.ndim(shape) else (shape,)))
     n = int(np.prod(shape))
     nbytes = max(1, n * dtype.itemsize)
-    raw = np.asarray(_Pinned(nbytes))
+    raw = np.asarray(_Pinned(nbytes, write_combined))
     return raw[: n * dtype.itemsize].view(dtype).reshape(shape)
 
 

@@ -400,6 +400,11 @@ int spx_host_alloc(void** out, size_t bytes) {
     SPX_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
     return SPX_OK;
 }
+int spx_host_alloc_wc(void** out, size_t bytes) {
+    if (!out) return spx_set_error(SPX_E_INVALID, "out is NULL");
+    SPX_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocWriteCombined));
+    return SPX_OK;
+}
 int spx_host_free(void* p) {
     if (p) SPX_CUDA(cudaFreeHost(p));
     return SPX_OK;

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "spx_plan.h"
+#include "spx_async.cuh"
 #include "spx_stft_device.cuh"
 #include "spx_tables.h"
 
@@ -72,20 +73,16 @@ struct BigCfg {
     static constexpr size_t smem_b() { return (size_t)(FPC * BUF2 + TW2) * 8 + (size_t)FPC * N2 * 8 + (size_t)N2 * TILE_LD * 4; }
 };
 
-// ---- cp.async (LDGSTS): every thread prefetches exactly the elements it will read back itself, so the staging
-// buffer needs no barrier -- it is a register-free prefetch of the next frame that overlaps the current transform
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
+// Prefetch of the next frame, two flavours (template parameter TMA):
+//   TMA  : bulk asynchronous copies (cp.async.bulk + mbarrier, SASS UBLKCP) -- one 128-byte row segment per thread in
+//          kernel A, one whole row per slot in kernel B; issued after the frame's first barrier (every thread has read
+//          the staging buffer by then).  Needs 16-byte aligned segments.
+//   !TMA : cp.async (LDGSTS) where every thread prefetches exactly the elements it will read back itself, so the
+//          staging buffer needs no barrier; used when frame starts are not 16-byte aligned.
 // ------------------------------------------------------------------ kernel A: column FFTs + twiddle
 // A CTA owns one group of G adjacent columns for all its frames (grid = groups x frame lanes), so the window
 // values and the W_N^{n2 k1} twiddles of a thread are frame-invariant and live in registers.
-template <int N1, int N2, int FMT>
+template <int N1, int N2, int FMT, bool TMA>
 __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A) big_cols_kernel(const BigParams p) {
     using C = BigCfg<N1, N2>;
     constexpr int N = C::N, T1 = C::T1, G = C::G, P = C::P1;
@@ -118,20 +115,38 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A) big_cols_kernel(con
             wn[u * RL + t] = cmul(__ldg(p.wn_coarse + (m >> 8)), __ldg(p.wn_fine + (m & 255u)));
         }
     const char* in_bytes = reinterpret_cast<const char*>(p.in);
+    __shared__ unsigned long long mbar_a;
+    const unsigned bar_u32 = smem_u32(&mbar_a);
+    const unsigned stage_u32 = smem_u32(stage);
     auto prefetch = [&](int f) {
-        const char* src = in_bytes + (size_t)(p.sample0 + (long long)f * p.hop + n2) * ELT;
+        if constexpr (TMA) {
+            // one bulk copy per row segment (G columns = G*ELT bytes), rows spread over the CTA's threads
+            const char* src0 = in_bytes + (size_t)(p.sample0 + (long long)f * p.hop + g * G) * ELT;
+            if (threadIdx.x == 0) mbar_expect_tx(bar_u32, (unsigned)(N1 * G * ELT));
+            for (int row = threadIdx.x; row < N1; row += C::THREADS_A)
+                bulk_g2s(stage_u32 + (unsigned)(row * G * ELT), src0 + (size_t)N2 * row * ELT, (unsigned)(G * ELT), bar_u32);
+        } else {
+            const char* src = in_bytes + (size_t)(p.sample0 + (long long)f * p.hop + n2) * ELT;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int row = tid + t * T1;
-            if (FMT == FMT_CF32) cp_async8(stage + (size_t)(row * G + c) * ELT, src + (size_t)N2 * row * ELT);
-            else                 cp_async4(stage + (size_t)(row * G + c) * ELT, src + (size_t)N2 * row * ELT);
+            for (int t = 0; t < 16; ++t) {
+                const int row = tid + t * T1;
+                if (FMT == FMT_CF32) cp_async8(stage + (size_t)(row * G + c) * ELT, src + (size_t)N2 * row * ELT);
+                else                 cp_async4(stage + (size_t)(row * G + c) * ELT, src + (size_t)N2 * row * ELT);
+            }
         }
     };
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) mbar_init(bar_u32, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     if (lane_f < p.frames) prefetch(lane_f);
     __syncthreads();  // twiddle table visible
+    unsigned parity = 0;
     float2 v[16];
     for (int f = lane_f; f < p.frames; f += lanes_f) {
-        cp_async_wait_all();
+        if constexpr (TMA) { mbar_wait(bar_u32, parity); parity ^= 1u; }
+        else cp_async_wait_all();
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int row = tid + t * T1;
@@ -140,11 +155,13 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A) big_cols_kernel(con
             else                 x = ci16_to_f2<TUNE_I2FP>(reinterpret_cast<const unsigned int*>(stage)[row * G + c]);
             v[t] = make_float2(x.x * w[t], x.y * w[t]);
         }
-        if (f + lanes_f < p.frames) prefetch(f + lanes_f);   // own slots only: overlaps the whole transform below
+        const bool more = f + lanes_f < p.frames;
+        if constexpr (!TMA) { if (more) prefetch(f + lanes_f); }   // own slots only: overlaps the whole transform below
         pass_dft<N1, 0>(v);
         if constexpr (P > 1) {
             pass_store_smem<N1, 0>(v, tid, bufA);
             __syncthreads();
+            if constexpr (TMA) { if (more) prefetch(f + lanes_f); }   // every thread has read the staging tile
             pass_load_smem<N1, 1>(v, tid, bufA);
             pass_twiddle_table<N1, 1, true>(v, tid, tws);
             pass_dft<N1, 1>(v);
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A) big_cols_kernel(con
 }
 
 // ------------------------------------------------------------------ kernel B: row FFTs + fused epilogue
-template <int N1, int N2, bool ACC>
+template <int N1, int N2, bool ACC, bool TMA>
 __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(const BigParams p) {
     using C = BigCfg<N1, N2>;
     constexpr int N = C::N, T2 = C::T2, FPC = C::FPC, P = C::P2, LD = C::TILE_LD;
@@ -190,12 +207,28 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(con
     const int chunks = (p.frames + p.frames_per_chunk - 1) / p.frames_per_chunk;
     const long long items = (long long)GROUPS * chunks;
     constexpr int SL = P - 1, RL = plan_radix(N2, SL), NB = 16 / RL;
+    __shared__ unsigned long long mbar_b[FPC];
+    const unsigned bar_u32 = smem_u32(&mbar_b[slot]);
+    const unsigned my_stage_u32 = smem_u32(my_stage);
     auto prefetch = [&](long long it, int f) {   // rows of frame f for item `it` (its row group)
         const int gg = (int)(it % GROUPS);
         const float2* row = p.scratch + (long long)f * N + (long long)(gg * FPC + slot) * N2;
+        if constexpr (TMA) {
+            if (tid == 0) {   // one bulk copy per slot: its whole N2-point row
+                mbar_expect_tx(bar_u32, (unsigned)(N2 * 8));
+                bulk_g2s(my_stage_u32, row, (unsigned)(N2 * 8), bar_u32);
+            }
+        } else {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) cp_async8(my_stage + tid + t * T2, row + tid + t * T2);
+            for (int t = 0; t < 16; ++t) cp_async8(my_stage + tid + t * T2, row + tid + t * T2);
+        }
     };
+    if constexpr (TMA) {
+        if (tid == 0) mbar_init(bar_u32, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+    unsigned parity = 0;
     StftAcc<ACC> acc;
     acc.reset();
     float2 v[16];
@@ -208,16 +241,21 @@ __global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_B) big_rows_kernel(con
         const int f_lo = ch * p.frames_per_chunk;
         const int f_hi = min(p.frames, f_lo + p.frames_per_chunk);
         for (int f = f_lo; f < f_hi; ++f) {
-            cp_async_wait_all();
+            if constexpr (TMA) { mbar_wait(bar_u32, parity); parity ^= 1u; }
+            else cp_async_wait_all();
 #pragma unroll
             for (int t = 0; t < 16; ++t) v[t] = my_stage[tid + t * T2];
             // next frame of this item, or the first frame of this CTA's next item
-            if (f + 1 < f_hi) prefetch(it, f + 1);
-            else if (it + gridDim.x < items) prefetch(it + gridDim.x, (int)((it + gridDim.x) / GROUPS) * p.frames_per_chunk);
+            auto prefetch_next = [&]() {
+                if (f + 1 < f_hi) prefetch(it, f + 1);
+                else if (it + gridDim.x < items) prefetch(it + gridDim.x, (int)((it + gridDim.x) / GROUPS) * p.frames_per_chunk);
+            };
+            if constexpr (!TMA) prefetch_next();
             pass_dft<N2, 0>(v);
             if constexpr (P > 1) {
                 pass_store_smem<N2, 0>(v, tid, bufA);
                 __syncthreads();
+                if constexpr (TMA) prefetch_next();   // every thread of the slot has read its staged row
                 pass_load_smem<N2, 1>(v, tid, bufA);
                 pass_twiddle_table<N2, 1, true>(v, tid, tws);
                 pass_dft<N2, 1>(v);
@@ -357,17 +395,28 @@ int bigfft_plan_init(spx_plan* pl) {
     return SPX_OK;
 }
 
+template <int N1, int N2, bool TMA_A>
+static int big_launch_pair_t(spx_plan* pl, BigParams& p, cudaStream_t st, bool acc, bool cf32);
+
 template <int N1, int N2>
 static int big_launch_pair(spx_plan* pl, BigParams& p, cudaStream_t st) {
-    using C = BigCfg<N1, N2>;
     const bool acc = p.welch_acc != nullptr || p.maxhold != nullptr;
     const bool cf32 = pl->cfg.in_fmt == SPX_FMT_CF32;
+    // bulk copies need 16-byte aligned row segments: every frame start must be 16-byte aligned
+    const size_t elt = cf32 ? 8 : 4;
+    const bool tma_a = ((uintptr_t)p.in & 15u) == 0 && ((size_t)p.hop * elt) % 16 == 0 && ((size_t)p.sample0 * elt) % 16 == 0;
+    return tma_a ? big_launch_pair_t<N1, N2, true>(pl, p, st, acc, cf32) : big_launch_pair_t<N1, N2, false>(pl, p, st, acc, cf32);
+}
+
+template <int N1, int N2, bool TMA_A>
+static int big_launch_pair_t(spx_plan* pl, BigParams& p, cudaStream_t st, bool acc, bool cf32) {
+    using C = BigCfg<N1, N2>;
     const size_t smem_a = C::smem_a(cf32 ? 8 : 4);
     const size_t smem_b = C::smem_b();
-    auto ka_c = big_cols_kernel<N1, N2, FMT_CF32>;
-    auto ka_i = big_cols_kernel<N1, N2, FMT_CI16>;
-    auto kb_a = big_rows_kernel<N1, N2, true>;
-    auto kb_n = big_rows_kernel<N1, N2, false>;
+    auto ka_c = big_cols_kernel<N1, N2, FMT_CF32, TMA_A>;
+    auto ka_i = big_cols_kernel<N1, N2, FMT_CI16, TMA_A>;
+    auto kb_a = big_rows_kernel<N1, N2, true, true>;    // the scratch rows are always 16-byte aligned
+    auto kb_n = big_rows_kernel<N1, N2, false, true>;
     static int occ_a[64][2] = {{0}}, occ_b[64][2] = {{0}};   // per device, benign race (same values)
     int dev = 0;
     SPX_CUDA(cudaGetDevice(&dev));

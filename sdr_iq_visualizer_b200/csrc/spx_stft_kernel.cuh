@@ -7,6 +7,7 @@
 // last FFT pass in fftshift order.
 #pragma once
 #include "spx_stft_device.cuh"
+#include "spx_async.cuh"
 #include "spx_internal.h"
 
 namespace spx {
@@ -40,34 +41,6 @@ __device__ __forceinline__ void slot_barrier(int slot) {
         const unsigned mask = (C::T >= 32 ? 0xffffffffu : ((1u << C::T) - 1u)) << lane0;
         __syncwarp(mask);
     }
-}
-
-// ---- mbarrier / bulk-copy (TMA) primitives
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-// (all take 32-bit shared-window addresses computed once, outside the frame loop)
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
 }
 
 // position of a worker (slot) in its frame sequence: chunks worker, worker + n_workers, ...

@@ -12,7 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sdr_iq_visualizer_b200 import _native as nat, spectral as sp, synth  # noqa: E402
 
 L, N, HOP = 61_440_000, 4096, 1024
-host_in = nat.pinned_empty(2 * L, np.int16)
+WC = os.environ.get("SPX_E2E_WC", "0") == "1"
+host_in = nat.pinned_empty(2 * L, np.int16, write_combined=WC)
 host_in[:] = synth.tiled_ci16(L, 2)
 F = nat.frame_count(L, N, HOP)
 h_wf = nat.pinned_empty((F, N), np.uint8)
@@ -30,7 +31,7 @@ for mib in [float(v) for v in (sys.argv[1:] or ["1", "2", "4", "8", "16", "32"])
         r = pl.stft(host_in, wf_rows=h_wf, welch=h_we, maxhold=h_mh, vmin=20.0, vmax=130.0)
         ts.append(time.perf_counter() - t0)
     med = float(np.median(ts))
-    print(json.dumps({"piece_mib": mib, "ms_med": round(med * 1e3, 3), "ms_best": round(min(ts) * 1e3, 3),
+    print(json.dumps({"wc_input": WC, "piece_mib": mib, "ms_med": round(med * 1e3, 3), "ms_best": round(min(ts) * 1e3, 3),
                       "GSps": round(L / med / 1e9, 2), "h2d_gbs": round(r.h2d_bytes / med / 1e9, 1),
                       "d2h_gbs": round(r.d2h_bytes / med / 1e9, 1)}), flush=True)
     pl.close()
