@@ -251,14 +251,20 @@ def clear_plans() -> None:
         _plans.clear()
 
 
-def stream_frame(samples, sample_rate: float, center_freq: float, eps: float = DB_EPS_REFERENCE, device: int = 0):
+def stream_frame(samples, sample_rate: float, center_freq: float, eps: float = DB_EPS_REFERENCE, device: int = 0,
+                 wf_range=None):
     """Drop-in for the three hot lines of the reference stream loop (streamer.py:119-121):
-    returns ``(freqs, power_db)``, both float64[N] in fftshift order, for one rx buffer."""
+    returns ``(freqs, power_db)``, both float64[N] in fftshift order, for one rx buffer of any length.
+    With ``wf_range=(vmin, vmax)`` the same launch also emits the uint8 waterfall row of the frame and the
+    return value is ``(freqs, power_db, wf_row)``."""
     x = np.asarray(samples)
     n = x.shape[0]
     pl = get_plan(n, n, "rect", FMT_CF32, 1.0, eps, device)
-    res = pl.stft(x, db_rows=True)
-    return freq_axis(n, sample_rate, center_freq), res.db_rows[0].astype(np.float64)
+    if wf_range is None:
+        res = pl.stft(x, db_rows=True)
+        return freq_axis(n, sample_rate, center_freq), res.db_rows[0].astype(np.float64)
+    res = pl.stft(x, db_rows=True, wf_rows=True, vmin=float(wf_range[0]), vmax=float(wf_range[1]))
+    return freq_axis(n, sample_rate, center_freq), res.db_rows[0].astype(np.float64), res.wf_rows[0]
 
 
 def welch_psd(x, nfft: int = 1024, hop: Optional[int] = None, window="hann", sample_rate: float = 1.0,

@@ -57,6 +57,7 @@ class SDRDataStreamer:
         self.samples_processed = 0
         self.h2d_bytes = 0
         self._latest = None
+        self.waterfall_range = None   # (vmin_db, vmax_db): frames then also carry the uint8 waterfall row ('wf_row')
 
     # ------------------------------------------------------------------ radio control (host I/O)
     def connect(self):
@@ -121,10 +122,17 @@ class SDRDataStreamer:
     def process_buffer(self, samples):
         """One rx buffer -> the frame dict of streamer.py:123-130 (spectrum on the GPU)."""
         n = len(samples)
-        _, power_db = spectral.stream_frame(samples, self.sample_rate, self.center_freq)
+        wf_row = None
+        if self.waterfall_range is None:
+            _, power_db = spectral.stream_frame(samples, self.sample_rate, self.center_freq)
+        else:
+            _, power_db, wf_row = spectral.stream_frame(samples, self.sample_rate, self.center_freq,
+                                                        wf_range=self.waterfall_range)
         self.samples_processed += n
         self.h2d_bytes += n * 8
+        extra = {} if wf_row is None else {'wf_row': wf_row}
         return {
+            **extra,
             'time': time.time(),
             'samples': samples,
             'freqs': self._frequency_axis(n),

@@ -41,7 +41,10 @@ class WaterfallBlock:
                 self._count += 1
 
     def push_db(self, power_db) -> None:
-        """One float dB row (the frame dict's ``power_db``): quantised with the kernel's rule."""
+        """One float dB row from a frame dict that carries no ``wf_row`` (e.g. a dict built by other code): the
+        display quantisation ``clip(floor((dB - vmin) * 256 / (vmax - vmin)), 0, 255)`` of SURVEY A7 applied to the
+        ALREADY COMPUTED spectrum.  The streaming path does not come through here: with
+        ``SDRDataStreamer.waterfall_range`` set, the kernel emits the uint8 row itself and ``push_rows`` takes it."""
         q = np.floor((np.asarray(power_db, dtype=np.float64) - self.vmin) * (256.0 / (self.vmax - self.vmin)))
         self.push_rows(np.clip(np.nan_to_num(q, nan=0.0, posinf=255.0, neginf=0.0), 0, 255).astype(np.uint8)[None, :])
 
@@ -136,7 +139,10 @@ def dashboard_tick(data: Optional[dict], waterfall: WaterfallBlock, device: int 
     if data is None:
         return None
     samples, freqs, power_db = data['samples'], data['freqs'], data['power_db']
-    waterfall.push_db(power_db)
+    if data.get('wf_row') is not None:
+        waterfall.push_rows(data['wf_row'])      # quantised by the kernel (streamer.waterfall_range)
+    else:
+        waterfall.push_db(power_db)
     peaks = peak_markers(power_db, device=device)
     return {
         "time_ms": np.arange(len(samples)) / data['sample_rate'] * 1000,      # :114

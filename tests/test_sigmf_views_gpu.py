@@ -98,3 +98,26 @@ def test_dashboard_tick_views(mods, golden_classifier):
             f"Classification: {r['label']} (conf {r['confidence']:.2f})\nOBW20={ft['bandwidth_hz_20db'] / 1e6:.2f} MHz, "
             f"SNR={ft['snr_db']:.1f} dB" + ("\n- " + "\n- ".join(reasons) if reasons else "")), name
     clf._CLASS_HISTORY.clear(); clf._CONF_HISTORY.clear()
+
+
+def test_streamer_emits_kernel_quantised_waterfall_row(mods):
+    """With waterfall_range set, the frame dict of streamer.py:123-130 also carries the uint8 row produced by the same
+    launch, and the dashboard tick takes it as is."""
+    import sys
+    from unittest.mock import MagicMock
+    sys.modules.setdefault("adi", MagicMock())
+    _, views = mods
+    from app.sdr.streamer import SDRDataStreamer
+    rng = np.random.default_rng(5)
+    samples = (rng.integers(-2047, 2048, 4096) + 1j * rng.integers(-2047, 2048, 4096)).astype(np.complex128)
+    s = SDRDataStreamer(sample_rate=61_440_000)
+    plain = s.process_buffer(samples)
+    assert set(plain) == {"time", "samples", "freqs", "power_db", "sample_rate", "center_freq"}    # the reference's dict, unchanged
+    s.waterfall_range = (0.0, 130.0)
+    d = s.process_buffer(samples)
+    assert np.array_equal(d["power_db"], plain["power_db"]) and d["wf_row"].dtype == np.uint8
+    X = np.fft.fftshift(np.fft.fft(samples))
+    parity.check_u8(d["wf_row"][None, :], sref.amplitude_db(X)[None, :], 0.0, 130.0, what="stream wf_row")
+    wf = views.WaterfallBlock(4096, vmin=0.0, vmax=130.0)
+    t = views.dashboard_tick(d, wf)
+    assert np.array_equal(t["waterfall"]["z"][0], d["wf_row"])
