@@ -272,6 +272,11 @@ typedef struct {
     int64_t slot_samples;   /* capacity of one slot, >= nfft */
     int32_t want_wf_rows, want_db_rows, want_welch, want_maxhold;
     float vmin, vmax;
+    int32_t want_features;  /* per slot: Welch PSD in dB (mlab.psd normalisation with sample_rate) + the classifier
+                             * measurements of it (classifier.py:45-58), computed on the device right behind the STFT
+                             * kernel; needs want_welch */
+    int32_t reserved;
+    double sample_rate;     /* Fs of the PSD normalisation (want_features) */
 } spx_ring_config;
 
 typedef struct {
@@ -285,6 +290,8 @@ typedef struct {
     const double* welch_acc;
     const float* maxhold;
     int64_t h2d_bytes, d2h_bytes; /* bytes this slot moved over PCIe, each direction */
+    const double* pxx_db;         /* pinned host, [nfft] 10*log10 of the slot's Welch density (want_features) */
+    const spx_features* features; /* pinned host, measurements of pxx_db (want_features) */
 } spx_ring_result;
 
 typedef struct {

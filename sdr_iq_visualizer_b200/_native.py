@@ -67,13 +67,15 @@ class spx_features(C.Structure):
 class spx_ring_config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_slots", C.c_int32), ("slot_samples", C.c_int64),
                 ("want_wf_rows", C.c_int32), ("want_db_rows", C.c_int32), ("want_welch", C.c_int32),
-                ("want_maxhold", C.c_int32), ("vmin", C.c_float), ("vmax", C.c_float)]
+                ("want_maxhold", C.c_int32), ("vmin", C.c_float), ("vmax", C.c_float), ("want_features", C.c_int32),
+                ("reserved", C.c_int32), ("sample_rate", C.c_double)]
 
 
 class spx_ring_result(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_int32), ("seq", C.c_int64), ("n_frames", C.c_int64),
                 ("first_frame", C.c_int64), ("wf_rows", C.c_void_p), ("db_rows", C.c_void_p), ("welch_acc", C.c_void_p),
-                ("maxhold", C.c_void_p), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("maxhold", C.c_void_p), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("pxx_db", C.c_void_p),
+                ("features", C.c_void_p)]
 
 
 class spx_ring_stats_t(C.Structure):

@@ -145,7 +145,26 @@ def classify_signal_advanced(freqs, power_db):
     text as the reference (classifier.py:146-161)."""
     if len(freqs) == 0 or len(power_db) == 0:
         return dict(_NO_DATA)
-    m = measure(freqs, power_db)
+    return classify_from_measurements(freqs, measure(freqs, power_db), len(power_db))
+
+
+def with_hz(freqs, m: dict) -> dict:
+    """Hz quantities for measurements that came back without a peak list (the ingest ring computes them on the
+    device per Welch block): occupied bandwidths from the bin edges, peak-spacing sigma from its value in bins
+    (the frequency axis is uniform)."""
+    m = dict(m)
+    m["bw3"] = _span(freqs, m["first_3db"], m["last_3db"])
+    m["bw10"] = _span(freqs, m["first_10db"], m["last_10db"])
+    m["bw20"] = _span(freqs, m["first_20db"], m["last_20db"])
+    df = float(freqs[1] - freqs[0]) if len(freqs) > 1 else 0.0
+    m["peak_spacing_std_hz"] = float(m.get("peak_spacing_std_bins", 0.0)) * df
+    return m
+
+
+def classify_from_measurements(freqs, m: dict, n_bins: int):
+    """Label rules + temporal smoothing (classifier.py:60-161) on measurements already taken (``measure`` or
+    ``with_hz``): scalar host logic only."""
+    power_db = range(n_bins)   # only its length is used below
     v = _V()
     v.snr, v.sfm, v.kurt = float(m["snr_db"]), float(m["flatness"]), float(m["kurtosis"])
     v.bw3, v.bw10, v.bw20 = m["bw3"], m["bw10"], m["bw20"]

@@ -351,6 +351,12 @@ __global__ void welch_finalize_kernel(const double* __restrict__ acc, int n, dou
     if (pxx_db) pxx_db[i] = 10.0 * log10(v);
 }
 
+int welch_finalize_launch(const double* acc, int n, double inv_norm, double* pxx, double* pxx_db, cudaStream_t st) {
+    welch_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(acc, n, inv_norm, pxx, pxx_db);
+    SPX_CUDA(cudaGetLastError());
+    return SPX_OK;
+}
+
 }  // namespace spx
 
 using namespace spx;

@@ -53,6 +53,7 @@ int bigfft_plan_init(spx_plan* pl);
 int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
                          unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
                          float vmax, cudaStream_t st, int sys_atomics = 0);
+int welch_finalize_launch(const double* acc, int n, double inv_norm, double* pxx, double* pxx_db, cudaStream_t st);
 int bluestein_plan_init(spx_plan* pl);
 int bluestein_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
                             unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,

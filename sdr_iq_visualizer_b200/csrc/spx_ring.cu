@@ -24,8 +24,11 @@ struct RingSlot {
     float *d_db = nullptr, *h_db = nullptr;
     double *d_welch = nullptr, *h_welch = nullptr;
     float *d_max = nullptr, *h_max = nullptr;
+    double *d_pdb = nullptr, *h_pdb = nullptr;       // Welch PSD of the slot in dB (want_features)
+    spx_features *d_feat = nullptr, *h_feat = nullptr;
     cudaEvent_t e_h2d = nullptr, e_kernel = nullptr, e_done = nullptr;
     long long seq = -1, n_frames = 0, first_frame = 0, h2d_bytes = 0, d2h_bytes = 0;
+    bool has_features = false;
     int state = 0;                   // 0 free, 1 acquired (being filled), 2 committed (in flight / ready)
 };
 
@@ -60,6 +63,10 @@ static void ring_free(spx_ring* r) {
         if (s.h_welch) cudaFreeHost(s.h_welch);
         if (s.d_max) cudaFree(s.d_max);
         if (s.h_max) cudaFreeHost(s.h_max);
+        if (s.d_pdb) cudaFree(s.d_pdb);
+        if (s.h_pdb) cudaFreeHost(s.h_pdb);
+        if (s.d_feat) cudaFree(s.d_feat);
+        if (s.h_feat) cudaFreeHost(s.h_feat);
         if (s.e_h2d) cudaEventDestroy(s.e_h2d);
         if (s.e_kernel) cudaEventDestroy(s.e_kernel);
         if (s.e_done) cudaEventDestroy(s.e_done);
@@ -74,6 +81,8 @@ extern "C" int spx_ring_create(spx_ring** out, spx_plan* plan, const spx_ring_co
     if (cfg->n_slots < 2 || cfg->n_slots > 64) return spx_set_error(SPX_E_INVALID, "n_slots must be in [2, 64]");
     if (cfg->slot_samples < plan->cfg.nfft) return spx_set_error(SPX_E_INVALID, "slot_samples must be >= nfft");
     if (cfg->want_wf_rows && !(cfg->vmax > cfg->vmin)) return spx_set_error(SPX_E_INVALID, "wf rows need vmax > vmin");
+    if (cfg->want_features && (!cfg->want_welch || !(cfg->sample_rate > 0)))
+        return spx_set_error(SPX_E_INVALID, "want_features needs want_welch and a positive sample_rate");
     SPX_CUDA(cudaSetDevice(plan->cfg.device));
     spx_ring* r = new (std::nothrow) spx_ring();
     if (!r) return spx_set_error(SPX_E_NOMEM, "out of host memory");
@@ -103,6 +112,13 @@ extern "C" int spx_ring_create(spx_ring** out, spx_plan* plan, const spx_ring_co
         if (cfg->want_maxhold) {
             if ((e = cudaMalloc((void**)&s.d_max, N * sizeof(float))) != cudaSuccess) break;
             if ((e = cudaHostAlloc((void**)&s.h_max, N * sizeof(float), cudaHostAllocPortable)) != cudaSuccess) break;
+        }
+        if (cfg->want_features) {
+            if ((e = cudaMalloc((void**)&s.d_pdb, N * sizeof(double))) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&s.h_pdb, N * sizeof(double), cudaHostAllocPortable)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&s.d_feat, sizeof(spx_features))) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&s.h_feat, sizeof(spx_features), cudaHostAllocPortable)) != cudaSuccess) break;
+            memset(s.h_feat, 0, sizeof(spx_features));
         }
         if ((e = cudaEventCreateWithFlags(&s.e_h2d, cudaEventDisableTiming)) != cudaSuccess) break;
         if ((e = cudaEventCreateWithFlags(&s.e_kernel, cudaEventDisableTiming)) != cudaSuccess) break;
@@ -158,6 +174,13 @@ extern "C" int spx_ring_commit(spx_ring* r, int64_t n_samples) {
     if (s.d_welch) SPX_CUDA(cudaMemsetAsync(s.d_welch, 0, (size_t)N * sizeof(double), pl->s_compute));
     if (s.d_max) SPX_CUDA(cudaMemsetAsync(s.d_max, 0, (size_t)N * sizeof(float), pl->s_compute));
     SPX_TRY(stft_launch_device(pl, s.d_in, 1, 0, F, s.d_db, s.d_wf, nullptr, s.d_welch, s.d_max, r->cfg.vmin, r->cfg.vmax, pl->s_compute));
+    // classifier measurements of this slot's Welch block, right behind the STFT kernel on the same stream
+    const bool feats = s.d_feat != nullptr && F > 0;
+    if (feats) {
+        const double inv = 1.0 / ((double)F * r->cfg.sample_rate * pl->sum_w2);
+        SPX_TRY(welch_finalize_launch(s.d_welch, N, inv, nullptr, s.d_pdb, pl->s_compute));
+        SPX_TRY(spx_classify_features_dev(pl->cfg.device, s.d_pdb, 1, N, 1, N, s.d_feat, nullptr, 0, nullptr, pl->s_compute));
+    }
     // carry the unconsumed tail into the head of the next slot's device buffer
     const long long consumed = F * hop;
     const long long new_carry = avail - consumed;
@@ -172,6 +195,12 @@ extern "C" int spx_ring_commit(spx_ring* r, int64_t n_samples) {
     if (s.d_db && F) { SPX_CUDA(cudaMemcpyAsync(s.h_db, s.d_db, (size_t)F * N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += F * N * 4; }
     if (s.d_welch) { SPX_CUDA(cudaMemcpyAsync(s.h_welch, s.d_welch, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += N * 8; }
     if (s.d_max) { SPX_CUDA(cudaMemcpyAsync(s.h_max, s.d_max, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += N * 4; }
+    if (feats) {
+        SPX_CUDA(cudaMemcpyAsync(s.h_pdb, s.d_pdb, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_d2h));
+        SPX_CUDA(cudaMemcpyAsync(s.h_feat, s.d_feat, sizeof(spx_features), cudaMemcpyDeviceToHost, pl->s_d2h));
+        d2h += N * 8 + (long long)sizeof(spx_features);
+    }
+    s.has_features = feats;
     SPX_CUDA(cudaEventRecord(s.e_done, pl->s_d2h));
     s.seq = r->seq++;
     s.n_frames = F;
@@ -209,6 +238,8 @@ extern "C" int spx_ring_collect(spx_ring* r, spx_ring_result* out) {
     out->maxhold = s->h_max;
     out->h2d_bytes = s->h2d_bytes;
     out->d2h_bytes = s->d2h_bytes;
+    out->pxx_db = s->has_features ? s->h_pdb : nullptr;
+    out->features = s->has_features ? s->h_feat : nullptr;
     return SPX_OK;
 }
 

@@ -22,17 +22,19 @@ from . import _native as nat
 
 class StreamRing:
     def __init__(self, plan, n_slots: int = 4, slot_samples: int = 1 << 22, wf_rows: bool = True, db_rows: bool = False,
-                 welch: bool = True, maxhold: bool = True, vmin: float = -100.0, vmax: float = 0.0):
+                 welch: bool = True, maxhold: bool = True, vmin: float = -100.0, vmax: float = 0.0,
+                 features: bool = False, sample_rate: float = 0.0):
         self.plan = plan  # keep the plan alive
         self.nfft = plan.nfft
         self.slot_samples = int(slot_samples)
         self._dtype = np.int16 if plan.in_fmt == nat.FMT_CI16 else np.complex64
         self._per_sample = 2 if plan.in_fmt == nat.FMT_CI16 else 1
         cfg = nat.spx_ring_config(C.sizeof(nat.spx_ring_config), int(n_slots), self.slot_samples, int(wf_rows), int(db_rows),
-                                  int(welch), int(maxhold), float(vmin), float(vmax))
+                                  int(welch), int(maxhold), float(vmin), float(vmax), int(features), 0, float(sample_rate))
         h = C.c_void_p()
         nat.check(nat.lib().spx_ring_create(C.byref(h), plan._h, C.byref(cfg)))
         self._h = h
+        self._n_slots = int(n_slots)
         plan._rings.add(self)
 
     def close(self):
@@ -82,7 +84,12 @@ class StreamRing:
             buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
             return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
-        return {"seq": int(r.seq), "n_frames": F, "first_frame": int(r.first_frame),
+        feats = None
+        if r.features:
+            from .features import _to_dict
+            feats = _to_dict(nat.spx_features.from_address(r.features), None)
+        return {"features": feats, "pxx_db": view(r.pxx_db, (N,), np.float64),
+                "seq": int(r.seq), "n_frames": F, "first_frame": int(r.first_frame),
                 "wf_rows": view(r.wf_rows, (F, N), np.uint8), "db_rows": view(r.db_rows, (F, N), np.float32),
                 "welch_acc": view(r.welch_acc, (N,), np.float64), "maxhold": view(r.maxhold, (N,), np.float32),
                 "h2d_bytes": int(r.h2d_bytes), "d2h_bytes": int(r.d2h_bytes)}

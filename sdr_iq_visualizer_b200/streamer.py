@@ -111,6 +111,99 @@ class SDRDataStreamer:
                 time.sleep(min(base_delay * (2 ** (attempt - 1)), 5.0))
         return False
 
+    # ------------------------------------------------------------------ block mode: pinned-ring ingest
+    def enable_block_mode(self, nfft=4096, overlap=0.75, window="hann", frames_per_block=1024, n_slots=4,
+                          vmin=0.0, vmax=130.0, device=0):
+        """High-rate path next to the per-buffer dicts: every rx buffer is also written, as raw int16 I,Q, into a
+        page-locked ring slot; a full slot (``frames_per_block`` hops) goes H2D -> fused STFT -> D2H on three
+        streams while the next slot fills.  Each block yields its uint8 waterfall rows, Welch PSD, max-hold and the
+        classifier measurements (computed on the device behind the STFT kernel); ``get_latest_block()`` returns the
+        newest one, ``get_status()`` reports the PCIe byte counters.  The reference queues one dict per buffer
+        instead (streamer.py:123-131,186-194)."""
+        from .ring import StreamRing
+        hop = max(1, int(round(nfft * (1.0 - overlap))))
+        self._blk_plan = spectral.SpectralPlan(nfft, hop, window, spectral.FMT_CI16, device=device)
+        self._blk_ring = StreamRing(self._blk_plan, n_slots=n_slots, slot_samples=frames_per_block * hop, wf_rows=True,
+                                    welch=True, maxhold=True, vmin=vmin, vmax=vmax, features=True,
+                                    sample_rate=float(self.sample_rate))
+        self._blk_cfg = {"nfft": nfft, "hop": hop, "vmin": vmin, "vmax": vmax, "slot_samples": frames_per_block * hop}
+        self._blk_slot, self._blk_fill, self._blk_pending = None, 0, 0
+        self._blk_maxhold = np.zeros(nfft, np.float32)
+        self._blk_axis = spectral.freq_axis(nfft, self.sample_rate, self.center_freq)
+        self._latest_block = None
+        self.blocks_done = 0
+        return self
+
+    def disable_block_mode(self):
+        ring, plan = getattr(self, "_blk_ring", None), getattr(self, "_blk_plan", None)
+        self._blk_ring = self._blk_plan = None
+        if ring is not None:
+            ring.close()
+        if plan is not None:
+            plan.close()
+
+    def _publish_block(self):
+        """Collect the oldest finished slot (blocks only until ITS copies are done) and publish it."""
+        from . import classifier
+        blk = self._blk_ring.collect()
+        np.maximum(self._blk_maxhold, blk["maxhold"], out=self._blk_maxhold)        # running max-hold across blocks
+        out = {"time": time.time(), "seq": blk["seq"], "first_frame": blk["first_frame"], "n_frames": blk["n_frames"],
+               "freqs": self._blk_axis, "wf_rows": blk["wf_rows"].copy(), "welch_acc": blk["welch_acc"].copy(),
+               "maxhold": self._blk_maxhold.copy(), "pxx_db": None if blk["pxx_db"] is None else blk["pxx_db"].copy(),
+               "features": None, "classification": None, "vmin": self._blk_cfg["vmin"], "vmax": self._blk_cfg["vmax"]}
+        if blk["features"] is not None:
+            m = classifier.with_hz(self._blk_axis, blk["features"])
+            out["features"] = m
+            out["classification"] = classifier.classify_from_measurements(self._blk_axis, m, self._blk_cfg["nfft"])
+        self._blk_ring.release()
+        self._blk_pending -= 1
+        self._latest_block = out
+        self.blocks_done += 1
+
+    def _feed_ring(self, samples):
+        """Append one rx buffer to the ring as interleaved int16 (pyadi-iio hands back the raw integer counts as
+        complex128, streamer.py:114, so the conversion is exact)."""
+        x = np.asarray(samples)
+        iq = np.empty(2 * x.size, np.int16)
+        iq[0::2] = np.clip(x.real, -32768, 32767)
+        iq[1::2] = np.clip(x.imag, -32768, 32767)
+        cap = self._blk_cfg["slot_samples"]
+        pos = 0
+        while pos < x.size:
+            if self._blk_slot is None:
+                if self._blk_pending >= self._blk_ring_slots() - 1:
+                    self._publish_block()
+                self._blk_slot, self._blk_fill = self._blk_ring.acquire(), 0
+            take = min(x.size - pos, cap - self._blk_fill)
+            self._blk_slot[2 * self._blk_fill: 2 * (self._blk_fill + take)] = iq[2 * pos: 2 * (pos + take)]
+            self._blk_fill += take
+            pos += take
+            if self._blk_fill == cap:
+                self._blk_ring.commit(cap)
+                self._blk_slot = None
+                self._blk_pending += 1
+                if self._blk_pending >= 2:       # keep one block in flight, publish the one before it
+                    self._publish_block()
+        self.h2d_bytes += 4 * x.size
+
+    def _blk_ring_slots(self):
+        return int(self._blk_ring._n_slots)
+
+    def flush_blocks(self):
+        """Commit a partly filled slot and publish everything in flight (end of a capture)."""
+        if getattr(self, "_blk_ring", None) is None:
+            return
+        if self._blk_slot is not None and self._blk_fill:
+            self._blk_ring.commit(self._blk_fill)
+            self._blk_pending += 1
+        self._blk_slot = None
+        while self._blk_pending:
+            self._publish_block()
+
+    def get_latest_block(self):
+        """Newest finished block of the ring ingest, or None (``enable_block_mode`` first)."""
+        return getattr(self, "_latest_block", None)
+
     # ------------------------------------------------------------------ the hot path
     def _frequency_axis(self, n):
         key = (n, self.sample_rate, self.center_freq)
@@ -130,6 +223,8 @@ class SDRDataStreamer:
                                                         wf_range=self.waterfall_range)
         self.samples_processed += n
         self.h2d_bytes += n * 8
+        if getattr(self, "_blk_ring", None) is not None:
+            self._feed_ring(samples)
         extra = {} if wf_row is None else {'wf_row': wf_row}
         return {
             **extra,
@@ -217,6 +312,8 @@ class SDRDataStreamer:
             'compute_errors': self.compute_errors,
             'samples_processed': self.samples_processed,
             'h2d_bytes': self.h2d_bytes,
+            'blocks_done': getattr(self, 'blocks_done', 0),
+            'ring': self._blk_ring.stats() if getattr(self, '_blk_ring', None) is not None else None,
         }
 
     def _push(self, data):
