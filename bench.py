@@ -141,7 +141,7 @@ def barrier_max(dist, local, seconds):
     return float(t.item())
 
 
-def cpu_baseline_single(sample_log2=22):
+def cpu_baseline_single(sample_log2=26):
     from oracle import pipeline_ref
     x = synth_ci16(1 << sample_log2, seed=2)
     best = 1e30

@@ -5,6 +5,7 @@ tag=${1:-r01}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/tests_${tag}.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/tests_${tag}.log
 tail -3 gpurun_out/tests_${tag}.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${tag}.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_${tag}.log
 python bench.py > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; echo "bench rc=$?"; cat gpurun_out/bench_${tag}.json
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${tag}.json 2>&1; echo "ref rc=$?"; cat gpurun_out/bench_ref_${tag}.json
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_${tag}.log 2>&1 &&
