@@ -57,6 +57,52 @@ __device__ long long block_min_ll(long long v, long long* sh) {
 }
 __device__ long long block_max_ll(long long v, long long* sh) { return -block_min_ll(-v, sh); }
 
+__device__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    unsigned long long r = sh[l];   // FT / 32 == 32 partials: every warp reduces them redundantly, no third barrier
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, r, o); r = t > r ? t : r; }
+    return r;
+}
+// three sums at once (every thread gets the results)
+__device__ void block_sum3(double* v, double (*sh)[FT / 32]) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) v[q] = warp_sum(v[q]);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { sh[0][w] = v[0]; sh[1][w] = v[1]; sh[2][w] = v[2]; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) v[q] = warp_sum(sh[q][l]);
+}
+// eight integer minima at once
+__device__ void block_min8(int* v, int (*sh)[FT / 32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] = min(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sh[q][w] = v[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        int r = sh[q][l];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o));
+        v[q] = r;
+    }
+}
+
 // order-preserving map double -> uint64
 __device__ __forceinline__ unsigned long long key_of(double x) {
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
@@ -72,7 +118,10 @@ __global__ void __launch_bounds__(FT, 1)
 features_kernel(const T* __restrict__ data, int n, long long stride, spx_features* __restrict__ out,
                 int* __restrict__ peaks, int peaks_cap, const spx_feature_opts opts) {
     __shared__ double shd[FT / 32];
+    __shared__ double shd3[3][FT / 32];
     __shared__ long long shl[FT / 32];
+    __shared__ unsigned long long shu[FT / 32];
+    __shared__ int shi8[8][FT / 32];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int words[FT / 32];
     __shared__ unsigned long long s_prefix;
@@ -93,26 +142,21 @@ features_kernel(const T* __restrict__ data, int n, long long stride, spx_feature
         const double v = (double)x[i];
         if (v > vmax) { vmax = v; imax = i; }
         s1 += v;
-        double p = pow(10.0, v / 10.0);
-        p = p < 1e-15 ? 1e-15 : p;
-        slog += log(p);
+        // p = max(10^(v/10), 1e-15) and ln p (classifier.py:185-187): one exp; ln p is v ln(10)/10 unless clipped
+        const double lnp = v * 0.23025850929940456840;   // ln(10)/10
+        double p = exp(lnp);
+        const bool clipped = p < 1e-15;
+        p = clipped ? 1e-15 : p;
+        slog += clipped ? -34.538776394910684 : lnp;      // ln(1e-15)
         slin += p;
     }
-    // max with smallest index: pack (key, ~index) and take the max
-    const long long peak_key = block_max_ll((long long)(key_of(vmax) >> 1), shl);  // drop 1 bit: still monotone
-    // (two elements that differ only in the dropped lowest mantissa bit would tie; resolve exactly below)
-    double peak = -DBL_MAX;
-    {
-        // exact: reduce the true maximum among candidates whose truncated key equals the winner
-        const bool cand = (long long)(key_of(vmax) >> 1) == peak_key;
-        const long long k2 = cand ? (long long)(key_of(vmax) & 1ull) : -1;
-        const long long low = block_max_ll(k2, shl);
-        peak = val_of(((unsigned long long)peak_key << 1) | (unsigned long long)low);
-    }
+    // one combined block reduction: exact maximum (order-preserving 64-bit key), then first index of it, and the sums
+    const unsigned long long kmax = block_max_u64(key_of(vmax), shu);
+    const double peak = val_of(kmax);
     const int argmax = (int)block_min_ll(vmax == peak ? (long long)imax : (long long)0x7fffffff, shl);
-    const double sum_x = block_sum(s1, shd);
-    const double sum_log = block_sum(slog, shd);
-    const double sum_lin = block_sum(slin, shd);
+    double sums[3] = {s1, slog, slin};
+    block_sum3(sums, shd3);
+    const double sum_x = sums[0], sum_log = sums[1], sum_lin = sums[2];
     const double mu = sum_x / (double)n;
 
     // ---- pass 2: variance + occupied-bandwidth edges (classifier.py:163-170, 18-23)
@@ -131,10 +175,13 @@ features_kernel(const T* __restrict__ data, int n, long long stride, spx_feature
     }
     const double var = block_sum(s2, shd) / (double)n;
     const double sd = sqrt(var);
-    f3 = (int)block_min_ll(f3, shl);   l3 = (int)block_max_ll(l3, shl);
-    f10 = (int)block_min_ll(f10, shl); l10 = (int)block_max_ll(l10, shl);
-    f20 = (int)block_min_ll(f20, shl); l20 = (int)block_max_ll(l20, shl);
-    fs = (int)block_min_ll(fs, shl);   ls = (int)block_max_ll(ls, shl);
+    {
+        // eight integer min/max in one pass: minima as they are, maxima negated
+        int mm[8] = {f3, f10, f20, fs, -l3, -l10, -l20, -ls};
+        block_min8(mm, shi8);
+        f3 = mm[0]; f10 = mm[1]; f20 = mm[2]; fs = mm[3];
+        l3 = -mm[4]; l10 = -mm[5]; l20 = -mm[6]; ls = -mm[7];
+    }
 
     // ---- pass 3: kurtosis (classifier.py:191-198)
     double kurt = 0.0;
@@ -158,9 +205,17 @@ features_kernel(const T* __restrict__ data, int n, long long stride, spx_feature
         if (tid < 256) hist[tid] = 0u;
         __syncthreads();
         const unsigned long long prefix = s_prefix;
-        for (int i = tid; i < n; i += FT) {
-            const unsigned long long k = key_of((double)x[i]);
-            if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)(k >> shift) & 0xffu], 1u);
+        // histogram of the current digit, warp-aggregated: the first passes see only a handful of distinct digits
+        // (same sign / exponent), which would serialise thousands of shared-memory atomics on one address
+        for (int i0 = 0; i0 < n; i0 += FT) {
+            const int i = i0 + tid;
+            unsigned int d = 0xffffffffu;
+            if (i < n) {
+                const unsigned long long k = key_of((double)x[i]);
+                if ((k & mask) == prefix) d = (unsigned int)(k >> shift) & 0xffu;
+            }
+            const unsigned int peers = __match_any_sync(0xffffffffu, d);
+            if (d != 0xffffffffu && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned int)__popc(peers));
         }
         __syncthreads();
         if (tid < 32) {
@@ -191,6 +246,18 @@ features_kernel(const T* __restrict__ data, int n, long long stride, spx_feature
         }
         mask |= 0xffull << shift;
         __syncthreads();
+        if (s_cnt_eq == 1u && shift > 0) {
+            // a single element carries this prefix: it IS the order statistic; fetch its remaining digits directly
+            const unsigned long long prefix1 = s_prefix;
+            __syncthreads();
+            for (int i = tid; i < n; i += FT) {
+                const unsigned long long k = key_of((double)x[i]);
+                if ((k & mask) == prefix1) s_prefix = k;
+            }
+            if (tid == 0) s_rank = 0u;
+            __syncthreads();
+            break;
+        }
     }
     const unsigned long long klo = s_prefix;
     const double vlo = val_of(klo);

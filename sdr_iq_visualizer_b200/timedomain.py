@@ -46,13 +46,16 @@ def iq_hist2d(x, r: float, bins: int = 256, in_fmt: int = FMT_CF32, in_scale: fl
 
 
 def frame_stats(x, frame_len: int, hop: int = 0, in_fmt: int = FMT_CF32, in_scale: float = 1.0, device: int = 0,
-                stream: int = 0):
-    """(mean_pow, peak_pow): float32 [F] each, F = (n - frame_len)//hop + 1."""
+                stream: int = 0, out=None):
+    """(mean_pow, peak_pow): float32 [F] each, F = (n - frame_len)//hop + 1.  ``out=(mean, peak)`` reuses caller
+    buffers living where the input lives."""
     nat.require_device()
     hop = hop or frame_len
     keep, ptr, mem, n = _input(x, in_fmt)
     F = nat.frame_count(n, frame_len, hop)
-    if mem == MEM_HOST:
+    if out is not None:
+        mean, peak = out
+    elif mem == MEM_HOST:
         mean, peak = np.zeros(F, np.float32), np.zeros(F, np.float32)
     else:
         mean, peak = DeviceArray((F,), np.float32, device), DeviceArray((F,), np.float32, device)
