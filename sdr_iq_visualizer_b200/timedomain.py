@@ -16,9 +16,9 @@ from ._native import FMT_CF32, FMT_CI16, MEM_HOST, DeviceArray
 
 
 def _input(x, in_fmt):
-    if isinstance(x, DeviceArray) or (hasattr(x, "data_ptr") and hasattr(x, "is_cuda")):
+    if isinstance(x, (DeviceArray, nat.DeviceView)) or (hasattr(x, "data_ptr") and hasattr(x, "is_cuda")):
         ptr, mem = nat.as_ptr(x)
-        nbytes = x.nbytes if isinstance(x, DeviceArray) else x.numel() * x.element_size()
+        nbytes = x.nbytes if isinstance(x, (DeviceArray, nat.DeviceView)) else x.numel() * x.element_size()
         return x, ptr, mem, nbytes // (4 if in_fmt == FMT_CI16 else 8)
     a = np.asarray(x)
     if in_fmt == FMT_CI16:

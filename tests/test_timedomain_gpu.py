@@ -75,3 +75,25 @@ def test_frame_stats_overlap_and_edges(td):
     m_ref, p_ref = sref.frame_stats(sref.unpack_ci16(raw), 512, 512)
     np.testing.assert_allclose(mean, m_ref, rtol=2e-7)
     np.testing.assert_allclose(peak, p_ref, rtol=0)    # integers: exact
+
+
+def test_hist2d_packed_counters_do_not_overflow_and_large_tables_fall_back(td):
+    """Shared-memory path: every sample of a chunk in ONE bin (65 528 per chunk fits a 16-bit counter), odd bin
+    counts (last packed word half used), unaligned device-side start (scalar loads); bins = 512 exceeds shared memory
+    and takes the global-atomic kernel."""
+    n = 1_000_003
+    x = np.full(n, 0.3 - 0.2j, np.complex64)
+    h = td.iq_hist2d(x, 1.0, 256)
+    want = sref.iq_hist2d(x, 1.0, 256)
+    assert h.sum() == n and np.array_equal(h, want) and h.max() == n
+    rng = np.random.default_rng(8)
+    y = (0.5 * (rng.standard_normal(300_001) + 1j * rng.standard_normal(300_001))).astype(np.complex64)
+    for bins in (3, 255, 512):
+        assert np.array_equal(td.iq_hist2d(y, 2.0, bins), sref.iq_hist2d(y, 2.0, bins)), bins
+    assert np.array_equal(td.iq_hist2d(y[1:], 2.0, 256), sref.iq_hist2d(y[1:], 2.0, 256))   # host path re-stages: aligned again
+    from sdr_iq_visualizer_b200 import _native as nat
+    d = nat.DeviceArray.from_host(y)
+    off = nat.DeviceView(d.ptr + 8, (y.size - 1,), np.complex64)                              # 8-byte offset: not 16-byte aligned
+    got = td.iq_hist2d(off, 2.0, 256)
+    nat.device_sync(0)                                                                        # device-memory calls are asynchronous
+    assert np.array_equal(got.to_host(), sref.iq_hist2d(y[1:], 2.0, 256))

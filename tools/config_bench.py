@@ -22,13 +22,18 @@ except Exception:
 
 
 def timed(fn, stream=0, warmup=3, iters=10):
-    t = nat.DeviceTimer(0, stream)
+    """Median / best time of fn() in ms.  The time-domain and feature entry points launch on library-internal
+    (non-blocking) streams, so CUDA events on another stream would not bracket them: wall clock between device
+    synchronisations instead (a few microseconds of launch + sync overhead are included)."""
     for _ in range(warmup):
         fn()
+    nat.device_sync(0)
     ms = []
     for _ in range(iters):
-        t.start(); fn(); t.stop()
-        ms.append(t.elapsed_ms())
+        t0 = time.perf_counter()
+        fn()
+        nat.device_sync(0)
+        ms.append((time.perf_counter() - t0) * 1e3)
     return float(np.median(ms)), float(min(ms))
 
 
@@ -71,7 +76,7 @@ def c3():
         emit(case=f"C3 I/Q 256x256 histogram, 2^24 {name} samples (device-resident, input L2-warm)", kernel_us=round(med * 1e3, 2),
              GSps=round(L / (med * 1e-3) / 1e9, 1), bytes_per_sample=bps)
         # cold input: rotate over copies that together are several times the 126 MB L2 (no dirty lines left behind)
-        ncopy = 4 if fmt == sp.FMT_CF32 else 8
+        ncopy = 16
         copies = [dx] + [nat.DeviceArray.from_host(x) for _ in range(ncopy - 1)]
         state = {"i": 0}
 
