@@ -15,7 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libspx.so")
+LIB_PATH = os.environ.get("SPX_LIB") or os.path.join(CSRC, "libspx.so")   # SPX_LIB: an alternative build (kernel experiments)
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_NODEVICE, E_BUSY = 0, -1, -2, -3, -4, -5, -6
 WINDOW_RECT, WINDOW_HANN, WINDOW_BLACKMAN = 0, 1, 2
