@@ -19,6 +19,10 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// split-phase barrier among `count` threads: arrive now (release), wait later (acquire) with mbar_wait
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n"

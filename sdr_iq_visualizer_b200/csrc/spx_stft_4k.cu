@@ -13,6 +13,14 @@ int launch_stft_4k(StftLaunch& L) {
         case 5: return launch_stft_n<4096, TW_REG, 2, true>(L);   // same as 0
         case 6: return launch_stft_n<4096, TW_LDG, 2, true>(L);
         case 7: return launch_stft_n<4096, TW_HYB, 2, true>(L);   // pass-1 twiddles from smem, pass-2 from registers
+        case 11: {  // software-pipelined rows-only kernel (falls back to the default when accumulators are wanted / unaligned)
+            const bool acc = L.p.welch_acc != nullptr || L.p.maxhold != nullptr;
+            if (!acc && stage_ok(L)) {
+                return L.in_fmt == FMT_CF32 ? launch_stft_pipe_inst<4096, FMT_CF32, 2, TUNE_I2FP>(L)
+                                            : launch_stft_pipe_inst<4096, FMT_CI16, 2, TUNE_I2FP>(L);
+            }
+            return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);
+        }
         case 10: return launch_stft_n<4096, TW_HYB, 2, true, TUNE_I2FP>(L);
         case 9: return launch_stft_n<4096, TW_REG, 2, true>(L);   // int16 -> float with I2F.S16 (XU pipe)
         default: return spx_set_error(SPX_E_INVALID, "unknown kernel variant %d for nfft 4096", L.variant);

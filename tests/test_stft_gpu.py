@@ -68,7 +68,28 @@ def test_cf32_host_parity(sp, nfft, hop, kind):
     pl.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("fmt,hop,L", [(0, 4096, 4096 * 700 + 5), (0, 2048, 4096 + 2048 * 999), (1, 1024, 4096 + 1024 * 1500), (0, 4096, 4096)])
+def test_4096_pipelined_rows_only_kernel(sp, fmt, hop, L):
+    """variant 11: frame f+1's first pass overlapped with frame f's exchange (split-phase mbarriers); rows only.
+    Several frames per CTA, a ragged tail, and the single-frame case."""
+    n = 4096
+    x = sref.synth_iq(L, seed=41)
+    x = sref.to_ci16(x) if fmt else x.astype(np.complex64)
+    pl = sp.SpectralPlan(n, hop, "hann", fmt, variant=11)
+    ref = sp.SpectralPlan(n, hop, "hann", fmt, variant=0)
+    vmin, vmax = (0.0, 130.0) if fmt else (-60.0, 60.0)
+    r = pl.stft(x, db_rows=True, wf_rows=True, spectrum=True, vmin=vmin, vmax=vmax)
+    r0 = ref.stft(x, db_rows=True, wf_rows=True, spectrum=True, vmin=vmin, vmax=vmax)
+    assert r.n_frames == r0.n_frames == (L - n) // hop + 1
+    np.testing.assert_array_equal(r.spectrum, r0.spectrum)      # same per-thread arithmetic, different schedule
+    np.testing.assert_array_equal(r.db_rows, r0.db_rows)
+    np.testing.assert_array_equal(r.wf_rows, r0.wf_rows)
+    X = oracle_rows(x[: 2 * (n + 20 * hop)] if fmt else x[: n + 20 * hop], n, hop, "hann", fmt=fmt)
+    parity.check_db_rows(r.db_rows[: X.shape[0]], X.real**2 + X.imag**2, what="pipelined")
+    pl.close(); ref.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 def test_4096_kernel_variants_agree(sp, variant):
     n, hop = 4096, 1024
     x = sref.to_ci16(sref.synth_iq(n + 300 * hop, seed=77))
