@@ -107,8 +107,6 @@ int stft_launch_device(spx_plan* pl, const void* in, long long n_streams, long l
     L.p.db_eps = pl->cfg.db_eps;
     L.p.db_pw_min = pl->cfg.db_eps * pl->cfg.db_eps * 1099511627776.0f;  // (2^20 eps)^2
     L.p.sys_atomics = sys_atomics;
-    L.p.q_vmin = vmin;
-    L.p.q_scale = 256.0f / (vmax - vmin);
     L.p.q_a = (float)(3.01029995663981195214 * 256.0 / ((double)vmax - (double)vmin));  // 10 log10(2) * scale
     L.p.q_b = (float)(-(double)vmin * 256.0 / ((double)vmax - (double)vmin));
     L.nfft = pl->cfg.nfft;

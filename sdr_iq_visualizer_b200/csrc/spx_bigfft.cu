@@ -44,7 +44,7 @@ struct BigParams {
     float2* spec_rows;
     double* welch_acc;       // [N] of this stream
     float* maxhold;
-    float db_eps, db_pw_min, q_vmin, q_scale, q_a, q_b;
+    float db_eps, db_pw_min, q_a, q_b;
     int frames_per_chunk;    // kernel B: accumulator flush granularity
     int sys_atomics;         // accumulators may live on a peer GPU
 };
@@ -488,8 +488,6 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
     p.maxhold = maxhold;
     p.db_eps = pl->cfg.db_eps;
     p.db_pw_min = pl->cfg.db_eps * pl->cfg.db_eps * 1099511627776.0f;
-    p.q_vmin = vmin;
-    p.q_scale = 256.0f / (vmax - vmin);
     p.q_a = (float)(3.01029995663981195214 * 256.0 / ((double)vmax - (double)vmin));
     p.q_b = (float)(-(double)vmin * 256.0 / ((double)vmax - (double)vmin));
     p.sys_atomics = sys_atomics;

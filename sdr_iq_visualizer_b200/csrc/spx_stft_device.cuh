@@ -30,8 +30,7 @@ struct StftParams {
     float* maxhold;              // [n_streams][N]  max= |X|^2       (fftshift order) or nullptr
     float db_eps;                // 20*log10(|X| + db_eps)
     float db_pw_min;             // below this |X|^2 the eps term matters and the exact form is evaluated
-    float q_vmin, q_scale;       // u8 = sat(floor((db - vmin) * scale)), scale = 256/(vmax-vmin)
-    float q_a, q_b;              // the same map on log2|X|^2:  (db - vmin) * scale = q_a * log2|X|^2 + q_b
+    float q_a, q_b;              // u8 = sat(floor((dB - vmin) * 256/(vmax-vmin))) evaluated on y = log2|X|^2: q_a * y + q_b
     int sys_atomics;             // accumulators may live on a peer GPU: flush with system-scope atomics
     int frames_per_chunk;        // accumulator flush granularity (<= 256)
     int chunks_per_stream;
@@ -117,11 +116,8 @@ SPX_HD unsigned int sat_floor_u8(float q) {
 }
 #define SPX_DB_PER_LOG2 6.02059991327962390427f  // 20*log10(2)
 
-// 20*log10(|X| + eps) (streamer.py:121).  For |X|^2 >= pw_min = (2^20 eps)^2 the eps term changes the
-// result by < 1e-5 dB and 10*log10(|X|^2) is evaluated instead (one MUFU instead of two).
-SPX_HD float amp_db_fast(float pw) { return (0.5f * SPX_DB_PER_LOG2) * fast_log2(pw); }
-SPX_HD float amp_db_exact(float pw, float eps) { return SPX_DB_PER_LOG2 * fast_log2(fast_sqrt(pw) + eps); }
-
+// dB = 20*log10(|X| + eps) (streamer.py:121) is evaluated on y = log2|X|^2: for |X|^2 >= pw_min = (2^20 eps)^2 the eps
+// term changes the result by < 1e-5 dB and y = lg2(|X|^2) (one MUFU); below it y = 2 lg2(sqrt(|X|^2) + eps).
 // pre-floor colormap value from y = log2|X|^2 in one FMA: (dB - vmin) * scale = q_a * y + q_b
 SPX_HD float quant_pre(float y, float q_a, float q_b) {
 #ifdef __CUDA_ARCH__

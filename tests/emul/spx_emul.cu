@@ -101,8 +101,6 @@ extern "C" int spx_emul_stft(int nfft, int in_fmt, int tw_mode, const void* in, 
     p.maxhold = maxhold;
     p.db_eps = db_eps;
     p.db_pw_min = db_eps * db_eps * 1099511627776.0f;  // (2^20 eps)^2
-    p.q_vmin = vmin;
-    p.q_scale = 256.0f / (vmax - vmin);
     p.q_a = (float)(3.01029995663981195214 * 256.0 / ((double)vmax - (double)vmin));  // 10 log10(2) * scale
     p.q_b = (float)(-(double)vmin * 256.0 / ((double)vmax - (double)vmin));
     if (p.frames_per_stream == 0) return 0;
