@@ -54,7 +54,13 @@ struct BigCfg {
     static constexpr int N = N1 * N2;
     // kernel A
     static constexpr int T1 = N1 / 16;
-    static constexpr int G = N1 >= 1024 ? 8 : 16;              // columns per CTA
+#ifndef SPX_K2_G
+#define SPX_K2_G 16
+#endif
+#ifndef SPX_K2_THREADS_B
+#define SPX_K2_THREADS_B 128   // 128-thread row CTAs: twice as many independent barrier groups per SM (+2 % on the config-5 shape)
+#endif
+    static constexpr int G = N1 >= 1024 ? 8 : SPX_K2_G;        // columns per CTA
     static constexpr int THREADS_A = G * T1;
     static constexpr int P1 = plan_passes(N1);
     static constexpr int BUF1 = padded_size(N1) + (P1 >= 3 ? N1 : 0);
@@ -62,7 +68,7 @@ struct BigCfg {
     static constexpr int TW1 = plan_tw_size(N1);
     // kernel B
     static constexpr int T2 = N2 / 16;
-    static constexpr int FPC = N2 >= 1024 ? 4 : (256 / T2 > 32 ? 32 : 256 / T2);  // rows per CTA
+    static constexpr int FPC = N2 >= 1024 ? 4 : (SPX_K2_THREADS_B / T2 > 32 ? 32 : SPX_K2_THREADS_B / T2);  // rows per CTA
     static constexpr int THREADS_B = FPC * T2;
     static constexpr int P2 = plan_passes(N2);
     static constexpr int BUF2 = padded_size(N2) + (P2 >= 3 ? N2 : 0);
