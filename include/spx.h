@@ -164,8 +164,9 @@ typedef struct {
 SPX_API int spx_stft_exec(spx_plan* plan, spx_stft_args* args);
 
 /* Measurement helper: runs spx_stft_exec (SPX_MEM_DEVICE buffers only) warmup+iters times on the
- * launch stream, each bracketed by CUDA events; optionally writes a 256 MiB buffer before every
- * iteration to flush the 126 MB L2.  ms_each[iters] receives the device time of each timed launch. */
+ * launch stream, each bracketed by CUDA events; optionally READS a 256 MiB buffer before every
+ * iteration to flush the 126 MB L2 without leaving dirty lines behind.  ms_each[iters] receives the device time of
+ * each timed launch. */
 SPX_API int spx_stft_time(spx_plan* plan, spx_stft_args* args, int32_t warmup, int32_t iters, int32_t flush_l2,
                           float* ms_each);
 
