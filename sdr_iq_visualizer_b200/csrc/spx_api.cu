@@ -564,6 +564,8 @@ int spx_plan_destroy(spx_plan* pl) {
     for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
     if (pl->d_win) cudaFree(pl->d_win);
     if (pl->d_tw) cudaFree(pl->d_tw);
+    if (pl->s_big_aux) { cudaStreamSynchronize(pl->s_big_aux); cudaStreamDestroy(pl->s_big_aux); }
+    for (cudaEvent_t e : pl->ev_big) if (e) cudaEventDestroy(e);
     if (pl->d_big_tw) cudaFree(pl->d_big_tw);
     if (pl->d_blu) cudaFree(pl->d_blu);
     if (pl->blu_inner) spx_plan_destroy(pl->blu_inner);

@@ -401,21 +401,27 @@ int bigfft_plan_init(spx_plan* pl) {
     return SPX_OK;
 }
 
+// what runs between the two kernels of a pair: order the row kernel (stream st) behind the column kernel (stream sa)
+struct BigOrder {
+    cudaStream_t sa;
+    cudaEvent_t a_done;   // recorded on sa after the column kernel; st waits for it (nullptr: same stream, no event)
+};
+
 template <int N1, int N2, bool TMA_A>
-static int big_launch_pair_t(spx_plan* pl, BigParams& p, cudaStream_t st, bool acc, bool cf32);
+static int big_launch_pair_t(spx_plan* pl, BigParams& p, cudaStream_t st, bool acc, bool cf32, const BigOrder& ord);
 
 template <int N1, int N2>
-static int big_launch_pair(spx_plan* pl, BigParams& p, cudaStream_t st) {
+static int big_launch_pair(spx_plan* pl, BigParams& p, cudaStream_t st, const BigOrder& ord) {
     const bool acc = p.welch_acc != nullptr || p.maxhold != nullptr;
     const bool cf32 = pl->cfg.in_fmt == SPX_FMT_CF32;
     // bulk copies need 16-byte aligned row segments: every frame start must be 16-byte aligned
     const size_t elt = cf32 ? 8 : 4;
     const bool tma_a = ((uintptr_t)p.in & 15u) == 0 && ((size_t)p.hop * elt) % 16 == 0 && ((size_t)p.sample0 * elt) % 16 == 0;
-    return tma_a ? big_launch_pair_t<N1, N2, true>(pl, p, st, acc, cf32) : big_launch_pair_t<N1, N2, false>(pl, p, st, acc, cf32);
+    return tma_a ? big_launch_pair_t<N1, N2, true>(pl, p, st, acc, cf32, ord) : big_launch_pair_t<N1, N2, false>(pl, p, st, acc, cf32, ord);
 }
 
 template <int N1, int N2, bool TMA_A>
-static int big_launch_pair_t(spx_plan* pl, BigParams& p, cudaStream_t st, bool acc, bool cf32) {
+static int big_launch_pair_t(spx_plan* pl, BigParams& p, cudaStream_t st, bool acc, bool cf32, const BigOrder& ord) {
     using C = BigCfg<N1, N2>;
     const size_t smem_a = C::smem_a(cf32 ? 8 : 4);
     const size_t smem_b = C::smem_b();
@@ -449,9 +455,13 @@ static int big_launch_pair_t(spx_plan* pl, BigParams& p, cudaStream_t st, bool a
     if (lanes < 1) lanes = 1;
     if (lanes > p.frames) lanes = p.frames;
     const unsigned grid_a = (unsigned)(GROUPS_A * lanes);
-    if (cf32) ka_c<<<grid_a, C::THREADS_A, smem_a, st>>>(p);
-    else ka_i<<<grid_a, C::THREADS_A, smem_a, st>>>(p);
+    if (cf32) ka_c<<<grid_a, C::THREADS_A, smem_a, ord.sa>>>(p);
+    else ka_i<<<grid_a, C::THREADS_A, smem_a, ord.sa>>>(p);
     SPX_CUDA(cudaGetLastError());
+    if (ord.a_done) {
+        SPX_CUDA(cudaEventRecord(ord.a_done, ord.sa));
+        SPX_CUDA(cudaStreamWaitEvent(st, ord.a_done, 0));
+    }
     // kernel B: (row groups) x (frame chunks) work items, one resident wave; accumulators flush once per item
     const int groups = N1 / C::FPC;
     const int resident_b = pl->sm_count * occ_b[dev][acc ? 0 : 1];
@@ -473,10 +483,17 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
                          float vmax, cudaStream_t st, int sys_atomics) {
     const int n = pl->cfg.nfft;
     const size_t frame_bytes = (size_t)n * sizeof(float2);
-    long long fb = (long long)(pl->big_scratch_bytes / frame_bytes);
+    // two halves of the scratch: the column kernel of batch k+1 (aux stream) runs next to the row kernel of batch k, so
+    // the tail wave of one kernel is filled by the other instead of leaving SMs idle
+    long long fb = (long long)(pl->big_scratch_bytes / 2 / frame_bytes);
     if (fb < 1) fb = 1;
     if (fb > frames) fb = frames;
-    SPX_TRY(pl->st_big.reserve((size_t)fb * frame_bytes));
+    const bool two = frames > fb;
+    SPX_TRY(pl->st_big.reserve((size_t)fb * frame_bytes * (two ? 2 : 1)));
+    if (two && !pl->s_big_aux) {
+        SPX_CUDA(cudaStreamCreateWithFlags(&pl->s_big_aux, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : pl->ev_big) SPX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     BigParams p;
     memset(&p, 0, sizeof(p));
     p.in = in;
@@ -486,7 +503,6 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
     p.tw2 = pl->d_tw2;
     p.wn_fine = pl->d_wn_fine;
     p.wn_coarse = pl->d_wn_coarse;
-    p.scratch = (float2*)pl->st_big.ptr;
     p.db_rows = db_rows;
     p.wf_rows = wf_rows;
     p.spec_rows = spec_rows;
@@ -497,22 +513,36 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
     p.q_a = (float)(3.01029995663981195214 * 256.0 / ((double)vmax - (double)vmin));
     p.q_b = (float)(-(double)vmin * 256.0 / ((double)vmax - (double)vmin));
     p.sys_atomics = sys_atomics;
-    for (long long f0 = 0; f0 < frames; f0 += fb) {
+    if (two) {   // everything already queued on st (accumulator memsets, the previous call) comes first
+        SPX_CUDA(cudaEventRecord(pl->ev_big[0], st));
+        SPX_CUDA(cudaStreamWaitEvent(pl->s_big_aux, pl->ev_big[0], 0));
+    }
+    long long k = 0;
+    for (long long f0 = 0; f0 < frames; f0 += fb, ++k) {
+        const int b = (int)(k & 1);
         p.frames = (int)(frames - f0 < fb ? frames - f0 : fb);
         p.sample0 = f0 * pl->cfg.hop;
         p.row0 = row0 + f0;
+        p.scratch = (float2*)pl->st_big.ptr + (size_t)(two ? b : 0) * (size_t)fb * n;
+        BigOrder ord{st, nullptr};
+        if (two) {
+            ord.sa = pl->s_big_aux;
+            ord.a_done = pl->ev_big[1 + b];
+            if (k >= 2) SPX_CUDA(cudaStreamWaitEvent(pl->s_big_aux, pl->ev_big[3 + b], 0));   // rows of batch k-2 left this half
+        }
         int rc;
         switch (n) {
-            case 1 << 14: rc = big_launch_pair<128, 128>(pl, p, st); break;
-            case 1 << 15: rc = big_launch_pair<128, 256>(pl, p, st); break;
-            case 1 << 16: rc = big_launch_pair<256, 256>(pl, p, st); break;
-            case 1 << 17: rc = big_launch_pair<256, 512>(pl, p, st); break;
-            case 1 << 18: rc = big_launch_pair<512, 512>(pl, p, st); break;
-            case 1 << 19: rc = big_launch_pair<512, 1024>(pl, p, st); break;
-            case 1 << 20: rc = big_launch_pair<1024, 1024>(pl, p, st); break;
+            case 1 << 14: rc = big_launch_pair<128, 128>(pl, p, st, ord); break;
+            case 1 << 15: rc = big_launch_pair<128, 256>(pl, p, st, ord); break;
+            case 1 << 16: rc = big_launch_pair<256, 256>(pl, p, st, ord); break;
+            case 1 << 17: rc = big_launch_pair<256, 512>(pl, p, st, ord); break;
+            case 1 << 18: rc = big_launch_pair<512, 512>(pl, p, st, ord); break;
+            case 1 << 19: rc = big_launch_pair<512, 1024>(pl, p, st, ord); break;
+            case 1 << 20: rc = big_launch_pair<1024, 1024>(pl, p, st, ord); break;
             default: return spx_set_error(SPX_E_UNSUPPORTED, "nfft %d", n);
         }
         SPX_TRY(rc);
+        if (two) SPX_CUDA(cudaEventRecord(pl->ev_big[3 + b], st));
     }
     return SPX_OK;
 }

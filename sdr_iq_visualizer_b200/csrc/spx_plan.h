@@ -35,8 +35,10 @@ struct spx_plan {
     int big_n1 = 0, big_n2 = 0;
     float2* d_big_tw = nullptr;  // one allocation holding the four tables below
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_wn_fine = nullptr, *d_wn_coarse = nullptr;
-    size_t big_scratch_bytes = 192u << 20;  // frames per batch = scratch / (nfft * 8); measured best on B200 (T round-trips through HBM either way)
+    size_t big_scratch_bytes = 384u << 20;  // two halves of 192 MB: frames per batch = half / (nfft * 8); measured best on B200
     spx::DevBuf st_big;
+    cudaStream_t s_big_aux = nullptr;             // column kernels of batch k+1 run here, next to the row kernels of batch k
+    cudaEvent_t ev_big[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // entry, A done x2, B done x2
     // Bluestein path (nfft not a power of two, or < 16): inner power-of-two plan of length blu_m
     int blu_m = 0;
     spx_plan* blu_inner = nullptr;
