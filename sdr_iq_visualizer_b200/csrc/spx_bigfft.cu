@@ -88,8 +88,12 @@ struct BigCfg {
 // ------------------------------------------------------------------ kernel A: column FFTs + twiddle
 // A CTA owns one group of G adjacent columns for all its frames (grid = groups x frame lanes), so the window
 // values and the W_N^{n2 k1} twiddles of a thread are frame-invariant and live in registers.
+#ifndef SPX_K2_OCC_A
+#define SPX_K2_OCC_A 1
+#endif
 template <int N1, int N2, int FMT, bool TMA>
-__global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A) big_cols_kernel(const BigParams p) {
+__global__ void __launch_bounds__(BigCfg<N1, N2>::THREADS_A, (BigCfg<N1, N2>::THREADS_A <= 256 ? SPX_K2_OCC_A : 1))
+big_cols_kernel(const BigParams p) {
     using C = BigCfg<N1, N2>;
     constexpr int N = C::N, T1 = C::T1, G = C::G, P = C::P1;
     constexpr int ELT = FMT == FMT_CF32 ? 8 : 4;
