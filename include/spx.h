@@ -145,7 +145,7 @@ typedef struct {
     uint8_t* wf_rows;     /* [n_streams*F][nfft]  clip(floor((db-vmin)*256/(vmax-vmin)),0,255) (A7) */
     float* spec_rows;     /* [n_streams*F][nfft][2] complex spectrum, fftshift order (streamer.py:119) */
     double* welch_acc;    /* [n_streams][nfft]    sum over frames of |X|^2 (A8; mlab.psd numerator) */
-    float* maxhold;       /* [n_streams][nfft]    max over frames of |X|^2 (A8) */
+    float* maxhold;       /* [n_streams][nfft]    max over frames of |X|^2 (A8); NaN powers are skipped (fmax) */
     float vmin, vmax;     /* waterfall colour range in dB */
     void* stream;         /* cudaStream_t for SPX_MEM_DEVICE (NULL = the plan's compute stream) */
     int64_t n_frames_out; /* out: F */

@@ -375,3 +375,30 @@ def test_stream_frame_any_buffer_size(sp):
         assert np.array_equal(f, f_ref)
         X = np.fft.fftshift(np.fft.fft(s))
         parity.check_db_rows(p[None, :], (X.real**2 + X.imag**2)[None, :], what=f"stream N={n}")
+
+
+def test_non_finite_samples_and_extreme_values(sp):
+    """NaN / Inf samples poison exactly the frames that contain them (as np.fft.fft does); the uint8 index of a NaN bin
+    is 0; the max-hold skips NaN powers (fmax semantics, documented in spx.h); int16 full-scale values are exact."""
+    n, hop = 1024, 512
+    x = sref.synth_iq(n + hop * 9, seed=3).astype(np.complex64)
+    x[3 * hop + 5] = np.nan                                   # inside frames 2 and 3 only
+    pl = sp.SpectralPlan(n, hop, "hann")
+    r = pl.stft(x, db_rows=True, wf_rows=True, maxhold=True, vmin=-60.0, vmax=60.0)
+    bad = np.isnan(r.db_rows).all(axis=1)
+    assert list(np.flatnonzero(bad)) == [2, 3] and not np.isnan(r.db_rows[~bad]).any()
+    assert np.all(r.wf_rows[bad] == 0)
+    good = np.delete(np.arange(r.n_frames), [2, 3])
+    X = oracle_rows(x, n, hop, "hann")
+    parity.check_db_rows(r.db_rows[good], (X.real**2 + X.imag**2)[good], what="frames without NaN")
+    assert np.isfinite(r.maxhold).all()
+    parity.check_power(r.maxhold[0], (X.real**2 + X.imag**2)[good].max(axis=0), what="max-hold skips NaN frames")
+    pl.close()
+    # int16 extremes, maximum overlap (hop = 1) on a short input
+    raw = np.array([-32768, 32767] * 40 + [32767, -32768] * 40, np.int16)
+    pl = sp.SpectralPlan(64, 1, "rect", sp.FMT_CI16)
+    r = pl.stft(raw, spectrum=True, db_rows=True)
+    assert r.n_frames == 80 - 64 + 1
+    X = oracle_rows(raw, 64, 1, "rect", fmt=1)
+    assert np.abs(r.spectrum - X).max() <= 4e-6 * np.abs(X).max()
+    pl.close()
