@@ -147,6 +147,7 @@ _SIGNATURES = {
 }
 
 _lib = None
+_lib_error = None          # a failed build / load is remembered: later calls raise at once instead of re-running make
 _lock = threading.Lock()
 
 
@@ -158,7 +159,16 @@ def build(verbose: bool = False) -> str:
     if shutil.which("nvcc") is None:
         env["PATH"] = "/usr/local/cuda/bin:" + env.get("PATH", "")
     jobs = str(max(1, min(8, os.cpu_count() or 1)))
-    res = subprocess.run(["make", "-C", CSRC, "-j", jobs], env=env, capture_output=True, text=True)
+    # one builder at a time across processes (one process per GPU may start on a tree without the .so): an exclusive
+    # file lock around make; the Makefile links to a temporary name and renames, so a concurrent loader never sees a
+    # half-written library
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock_fh:
+        fcntl.flock(lock_fh, fcntl.LOCK_EX)
+        try:
+            res = subprocess.run(["make", "-C", CSRC, "-j", jobs], env=env, capture_output=True, text=True)
+        finally:
+            fcntl.flock(lock_fh, fcntl.LOCK_UN)
     if verbose or res.returncode != 0:
         print(res.stdout[-4000:])
         print(res.stderr[-4000:])
@@ -169,24 +179,37 @@ def build(verbose: bool = False) -> str:
 
 def lib() -> C.CDLL:
     """Load (building on first use if the .so is absent) and type the library."""
-    global _lib
+    global _lib, _lib_error
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            build()
+        if _lib_error is not None:      # do not rebuild / reload per call (e.g. per rx buffer in the streaming thread)
+            raise SpectralError(E_UNSUPPORTED, _lib_error)
         try:
+            if not os.path.exists(LIB_PATH):
+                build()
             handle = C.CDLL(LIB_PATH)
+        except SpectralError as e:
+            _lib_error = f"libspx.so unavailable (cached failure; call _native.reset_load_failure() to retry): {e}"
+            raise
         except OSError as e:  # missing extension is fatal: no fallback path exists
-            raise SpectralError(E_UNSUPPORTED, f"cannot load {LIB_PATH}: {e}") from e
+            _lib_error = f"cannot load {LIB_PATH} (cached failure; call _native.reset_load_failure() to retry): {e}"
+            raise SpectralError(E_UNSUPPORTED, _lib_error) from e
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def reset_load_failure() -> None:
+    """Forget a cached build / load failure so that the next call tries again (after fixing the toolchain)."""
+    global _lib_error
+    with _lock:
+        _lib_error = None
 
 
 def last_error() -> str:

@@ -49,6 +49,25 @@ def freq_axis(nfft: int, sample_rate: float, center_freq: float = 0.0) -> np.nda
     return np.fft.fftshift(np.fft.fftfreq(int(nfft), 1 / sample_rate)) + center_freq
 
 
+def _buffer_dtype_count(buf):
+    """(numpy dtype, element count) of a numpy array, DeviceArray / DeviceView or torch tensor."""
+    if isinstance(buf, np.ndarray):
+        return buf.dtype, int(buf.size)
+    if isinstance(buf, (DeviceArray, nat.DeviceView)):
+        return np.dtype(buf.dtype), int(np.prod(buf.shape))
+    if hasattr(buf, "data_ptr"):   # torch tensor: "torch.float32" -> float32
+        return np.dtype(str(buf.dtype).replace("torch.", "")), int(buf.numel())
+    raise TypeError(f"unsupported buffer type {type(buf)!r}")
+
+
+def _check_buffer(buf, shape, dtype, name: str) -> None:
+    """Caller-supplied output buffer: dtype and element count must be exactly what libspx will write."""
+    want_dt, want_n = np.dtype(dtype), int(np.prod(shape))
+    dt, n = _buffer_dtype_count(buf)
+    if dt != want_dt or n != want_n:
+        raise ValueError(f"{name}: expected {want_n} elements of {want_dt} (shape {tuple(shape)}), got {n} of {dt}")
+
+
 @dataclass
 class StftResult:
     n_frames: int
@@ -156,21 +175,27 @@ class SpectralPlan:
         rows = n_streams * F
         N = self.nfft
 
-        def out(flag, shape, dtype):
+        def out(flag, shape, dtype, name, accumulator=False):
             if flag is False or flag is None:
                 return None
             if flag is True:
-                return np.empty(shape, dtype) if mem == MEM_HOST else DeviceArray(shape, dtype, self.device)
+                # library-allocated accumulators start from zero (``accumulate=True`` then means "add to nothing")
+                if mem == MEM_HOST:
+                    return np.zeros(shape, dtype) if accumulator else np.empty(shape, dtype)
+                return DeviceArray(shape, dtype, self.device, zero=accumulator)
             p, m = nat.as_ptr(flag)
             if m != mem:
                 raise ValueError("output buffers must live where the input lives")
+            # libspx writes prod(shape) elements of ITS type through this pointer: a buffer of another size or dtype
+            # would be overrun (or half filled) silently, so it is refused here
+            _check_buffer(flag, shape, dtype, name)
             return flag
 
-        o_db = out(db_rows, (rows, N), np.float32)
-        o_wf = out(wf_rows, (rows, N), np.uint8)
-        o_sp = out(spectrum, (rows, N), np.complex64)
-        o_we = out(welch, (n_streams, N), np.float64)
-        o_mh = out(maxhold, (n_streams, N), np.float32)
+        o_db = out(db_rows, (rows, N), np.float32, "db_rows")
+        o_wf = out(wf_rows, (rows, N), np.uint8, "wf_rows")
+        o_sp = out(spectrum, (rows, N), np.complex64, "spectrum")
+        o_we = out(welch, (n_streams, N), np.float64, "welch", accumulator=True)
+        o_mh = out(maxhold, (n_streams, N), np.float32, "maxhold", accumulator=True)
         a = nat.spx_stft_args()
         a.struct_size = C.sizeof(nat.spx_stft_args)
         a.mem = mem
@@ -218,6 +243,12 @@ class SpectralPlan:
         ``welch_acc``) to avoid an allocation per call."""
         p, mem = nat.as_ptr(welch_acc)
         N = self.nfft * int(n_streams)
+        _check_buffer(welch_acc, (N,), np.float64, "welch_acc")
+        for name, buf in (("pxx", pxx), ("pdb", pdb)):
+            if buf is not None:
+                if nat.as_ptr(buf)[1] != mem:
+                    raise ValueError(f"{name} must live where welch_acc lives")
+                _check_buffer(buf, (N,), np.float64, name)
         if mem == MEM_HOST:
             pxx = np.empty(N, np.float64) if pxx is None else pxx
             pdb = (np.empty(N, np.float64) if want_db else None) if pdb is None else pdb

@@ -12,11 +12,14 @@ float64[N] in fftshift order.  ``import adi`` stays at module top so tests can m
 Changed on purpose:
   * the three numpy lines (streamer.py:119-121) are one call into ``spectral.stream_frame`` (CUDA);
     the frequency axis is cached per (N, fs, fc) instead of being rebuilt per buffer;
-  * a compute failure raises ``SpectralError`` and is logged and counted separately -- it no longer
-    looks like a radio fault and never triggers a reconnect (reference :157-174 would);
-  * ``get_latest_data()`` returns the NEWEST queued frame (the reference pops the oldest, SURVEY.md
-    section 0);
-  * ``get_status()`` also reports compute errors, samples processed and H2D bytes.
+  * any exception raised after ``rx()`` returned (``SpectralError``, but also a ``ValueError`` or ``TypeError``
+    out of the processing) is a COMPUTE fault: logged rate-limited, counted separately, backed off and, after
+    ``COMPUTE_FAULT_LIMIT`` in a row, the stream stops with ``compute_state == 'failed'`` -- it never looks like a
+    radio fault and never triggers a reconnect (reference :157-174 would);
+  * ``get_latest_data()`` keeps the reference's pop-one (oldest first) semantics so that unmodified consumers
+    share the queue as before; ``get_newest_data()`` / ``get_latest_data(drain=True)`` discard stale frames and
+    ``peek_latest()`` does not consume at all;
+  * ``get_status()`` also reports the compute state, compute errors, samples processed and H2D bytes.
 """
 import logging
 import queue
@@ -260,12 +263,15 @@ class SDRDataStreamer:
             try:
                 samples = self.sdr.rx()  # blocking hardware read
                 radio_errors, backoff = 0, 0.1
+                # everything after rx() is compute: ANY exception from it (SpectralError, but also a ValueError /
+                # TypeError / KeyError out of process_buffer or the ring feed) is a compute fault, never a radio fault
                 try:
                     frame = self.process_buffer(samples)
-                except SpectralError as exc:
-                    self.compute_errors += 1
-                    logger.error("GPU spectrum failed (not a radio fault): %s", exc)
+                except Exception as exc:
+                    if not self._compute_fault(exc):
+                        break
                     continue
+                self._compute_ok()
                 self._push(frame)
                 self.last_success_ts = frame['time']
                 self.total_frames += 1
@@ -300,6 +306,33 @@ class SDRDataStreamer:
                     self.running = False
                     break
 
+    # ------------------------------------------------------------------ compute-fault handling
+    COMPUTE_FAULT_LIMIT = 25        # consecutive failures after which the stream stops ("failed")
+    COMPUTE_BACKOFF_MAX_S = 1.6
+
+    def _compute_fault(self, exc) -> bool:
+        """Count a compute failure, log it rate-limited, back off; returns False when the stream must stop."""
+        self.compute_errors += 1
+        self.compute_errors_consecutive = getattr(self, 'compute_errors_consecutive', 0) + 1
+        k = self.compute_errors_consecutive
+        self.compute_last_error = f"{type(exc).__name__}: {exc}"
+        self.compute_state = 'degraded'
+        if k == 1 or k % 10 == 0:
+            logger.error("GPU spectrum failed (not a radio fault; %d in a row): %s", k, self.compute_last_error)
+        if k >= self.COMPUTE_FAULT_LIMIT:
+            logger.error("GPU spectrum failed %d times in a row; stopping the stream (radio left connected).", k)
+            self.compute_state = 'failed'
+            self.running = False
+            return False
+        time.sleep(min(0.05 * (2 ** min(k - 1, 5)), self.COMPUTE_BACKOFF_MAX_S))
+        return True
+
+    def _compute_ok(self) -> None:
+        if getattr(self, 'compute_errors_consecutive', 0):
+            logger.info("GPU spectrum recovered after %d failures.", self.compute_errors_consecutive)
+        self.compute_errors_consecutive = 0
+        self.compute_state = 'ok'
+
     # ------------------------------------------------------------------ queue + status
     def get_status(self):
         last = getattr(self, 'last_success_ts', None)
@@ -310,6 +343,9 @@ class SDRDataStreamer:
             'last_success_age_ms': (time.time() - last) * 1000 if last else None,
             'total_frames': getattr(self, 'total_frames', 0),
             'compute_errors': self.compute_errors,
+            'compute_state': getattr(self, 'compute_state', 'ok'),          # ok | degraded (backing off) | failed (stopped)
+            'compute_errors_consecutive': getattr(self, 'compute_errors_consecutive', 0),
+            'compute_last_error': getattr(self, 'compute_last_error', None),
             'samples_processed': self.samples_processed,
             'h2d_bytes': self.h2d_bytes,
             'blocks_done': getattr(self, 'blocks_done', 0),
@@ -329,8 +365,16 @@ class SDRDataStreamer:
                 except queue.Empty:
                     return
 
-    def get_latest_data(self):
-        """Newest queued frame or None (older frames are discarded)."""
+    def get_latest_data(self, drain: bool = False):
+        """Reference semantics by default (streamer.py:196-200): pop ONE frame, the oldest queued, or None when the
+        queue is empty -- unmodified consumers (dashboard tick callbacks.py:104, recorder callbacks.py:263, chatbot
+        chatbot.py:149) share this call and must not starve each other.  ``drain=True`` discards everything but the
+        newest frame and returns it (see also ``get_newest_data`` / ``peek_latest``)."""
+        if not drain:
+            try:
+                return self.data_queue.get_nowait()
+            except queue.Empty:
+                return None
         latest = None
         while True:
             try:
@@ -338,6 +382,9 @@ class SDRDataStreamer:
             except queue.Empty:
                 return latest
 
+    def get_newest_data(self):
+        """Newest queued frame (older ones are discarded), or None."""
+        return self.get_latest_data(drain=True)
 
     def peek_latest(self):
         """Newest frame WITHOUT consuming the queue: a second consumer (the chatbot's classify tool,

@@ -40,6 +40,8 @@ def iq_hist2d(x, r: float, bins: int = 256, in_fmt: int = FMT_CF32, in_scale: fl
     optr, omem = nat.as_ptr(out)
     if omem != mem:
         raise ValueError("output must live where the input lives")
+    from .spectral import _check_buffer
+    _check_buffer(out, (bins, bins), np.uint32, "out")
     nat.check(nat.lib().spx_iq_hist2d(device, mem, ptr, in_fmt, float(in_scale), n, float(r), int(bins), optr,
                                       1 if accumulate else 0, stream or None))
     return out
@@ -55,6 +57,11 @@ def frame_stats(x, frame_len: int, hop: int = 0, in_fmt: int = FMT_CF32, in_scal
     F = nat.frame_count(n, frame_len, hop)
     if out is not None:
         mean, peak = out
+        from .spectral import _check_buffer
+        for name, buf in (("mean", mean), ("peak", peak)):
+            if nat.as_ptr(buf)[1] != mem:
+                raise ValueError(f"out {name} must live where the input lives")
+            _check_buffer(buf, (F,), np.float32, "out " + name)
     elif mem == MEM_HOST:
         mean, peak = np.zeros(F, np.float32), np.zeros(F, np.float32)
     else:

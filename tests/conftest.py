@@ -42,3 +42,19 @@ def golden_classifier():
     with open(os.path.join(GOLDEN, "classifier_cases.json")) as fh:
         res = json.load(fh)
     return z, res
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Observed parity margins of this session -> gpurun_out/parity_margins.json (the GPU box only brings gpurun_out/ back;
+    the committed copy is profiles/r02_parity_margins.json)."""
+    try:
+        from tests import parity
+        if not parity.MARGINS:
+            return
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "parity_margins.json"), "w") as fh:
+            json.dump({"tolerances": {"db_above_floor": parity.DB_TOL, "rel": parity.REL_TOL, "u8_tie": parity.TIE_TOL},
+                       "checks": parity.MARGINS}, fh, indent=1)
+    except Exception:
+        pass

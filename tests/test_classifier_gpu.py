@@ -65,6 +65,29 @@ def test_temporal_smoothing_sequence(clf, golden_classifier):
     _clear(clf)
 
 
+def test_reference_test_classifier_runs_unchanged(clf):
+    """The reference's own tests/test_classifier.py (vendored byte for byte as tests/golden/reference_test_classifier.py,
+    /root/reference/tests/test_classifier.py:1-63) executed against `app.processing.classifier` of this repo."""
+    import hashlib
+    import importlib.util
+    import os
+    import unittest
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_test_classifier.py")
+    with open(path, "rb") as fh:
+        assert hashlib.sha256(fh.read()).hexdigest() == "81b5422a44e9c1b337f15d66b1cca256576cb665007569d4318e57a9e3123678", "vendored reference test was edited"
+    spec = importlib.util.spec_from_file_location("reference_test_classifier", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)           # imports app.processing.classifier -> the CUDA-backed drop-in
+    import app.processing.classifier as served
+    assert mod.classify_signal_advanced is served.classify_signal_advanced
+    _clear(clf)
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+    assert suite.countTestCases() == 5
+    result = unittest.TextTestRunner(verbosity=0).run(suite)
+    assert result.wasSuccessful(), (result.failures, result.errors)
+    _clear(clf)
+
+
 def test_reference_unit_tests_restated(clf):
     """The assertions of the reference's tests/test_classifier.py:7-60, on the drop-in."""
     assert clf.classify_signal_simple(np.array([]), np.array([])) == "No Data"

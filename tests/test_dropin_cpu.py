@@ -66,7 +66,9 @@ def test_streamer_drop_in_surface():
     for i in range(130):                       # drop-oldest bounded queue
         s._push({"i": i})
     assert s.data_queue.qsize() == 100
-    assert s.get_latest_data() == {"i": 129} and s.get_latest_data() is None
+    # reference semantics (streamer.py:196-200): one frame per call, oldest first; the newest only on request
+    assert s.get_latest_data() == {"i": 30} and s.get_latest_data() == {"i": 31}
+    assert s.get_newest_data() == {"i": 129} and s.get_latest_data() is None
     st = s.get_status()
     assert {"connected", "running", "queue_size", "last_success_age_ms", "total_frames"} <= set(st)
 
@@ -93,6 +95,42 @@ def test_streamer_compute_error_is_not_a_radio_fault(monkeypatch):
     s.sdr, s.connected, s.running = Radio(), True, True
     s._stream_data()
     assert s.compute_errors == 5 and s.total_frames == 0 and s.connected is True
+    assert s.get_status()["compute_state"] == "degraded" and "injected" in s.get_status()["compute_last_error"]
+
+
+def test_streamer_any_processing_exception_is_a_compute_fault_and_stops_after_limit(monkeypatch):
+    """A ValueError out of process_buffer is not a radio fault either; the stream stops after COMPUTE_FAULT_LIMIT
+    consecutive compute failures instead of spinning, and says so in get_status()."""
+    sys.modules.setdefault("adi", MagicMock())
+    from sdr_iq_visualizer_b200 import streamer as st
+    s = st.SDRDataStreamer()
+    s.COMPUTE_FAULT_LIMIT = 4
+    monkeypatch.setattr(st.time, "sleep", lambda *_: None)
+
+    class Radio:
+        def rx(self_inner):
+            return np.zeros(64, complex)
+
+    monkeypatch.setattr(s, "process_buffer", lambda *_: (_ for _ in ()).throw(ValueError("bad shape")))
+    monkeypatch.setattr(s, "_attempt_reconnect", lambda *a, **k: pytest.fail("reconnect attempted"))
+    s.sdr, s.connected, s.running = Radio(), True, True
+    s._stream_data()
+    st_ = s.get_status()
+    assert s.running is False and s.connected is True
+    assert st_["compute_state"] == "failed" and st_["compute_errors"] == 4 and "ValueError" in st_["compute_last_error"]
+
+
+def test_two_consumers_share_the_queue_like_the_reference():
+    """Dashboard tick (callbacks.py:104) and chatbot tool (chatbot.py:149) both call get_latest_data(): each call
+    consumes one frame, so a second consumer still finds data after the first one ran."""
+    sys.modules.setdefault("adi", MagicMock())
+    from app.sdr.streamer import SDRDataStreamer
+    s = SDRDataStreamer()
+    for i in range(3):
+        s._push({"i": i})
+    assert s.get_latest_data() == {"i": 0}      # dashboard
+    assert s.get_latest_data() == {"i": 1}      # chatbot right after it: not starved
+    assert s.peek_latest() == {"i": 2} and s.data_queue.qsize() == 1
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
@@ -104,3 +142,53 @@ def test_reference_streamer_suite_passes_on_drop_in():
                          cwd=ROOT, env=env, capture_output=True, text=True)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "6 passed" in res.stdout
+
+
+def test_vendored_reference_test_is_verbatim():
+    """tests/golden/reference_test_classifier.py is the reference's tests/test_classifier.py byte for byte (checked when
+    /root/reference is present, i.e. in the build container)."""
+    import os
+    ref = "/root/reference/tests/test_classifier.py"
+    if not os.path.exists(ref):
+        import pytest
+        pytest.skip("reference tree not present on this box")
+    here = os.path.join(os.path.dirname(__file__), "golden", "reference_test_classifier.py")
+    with open(ref, "rb") as a, open(here, "rb") as b:
+        assert a.read() == b.read()
+
+
+def test_failed_library_load_is_cached(monkeypatch, tmp_path):
+    """A missing / unbuildable libspx.so raises at once on every later call instead of re-running make per call."""
+    from sdr_iq_visualizer_b200 import _native as nat
+    calls = {"n": 0}
+
+    def failing_build(*a, **k):
+        calls["n"] += 1
+        raise nat.SpectralError(nat.E_UNSUPPORTED, "injected build failure")
+
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "_lib_error", None)
+    monkeypatch.setattr(nat, "LIB_PATH", str(tmp_path / "absent.so"))
+    monkeypatch.setattr(nat, "build", failing_build)
+    for _ in range(3):
+        with pytest.raises(nat.SpectralError):
+            nat.lib()
+    assert calls["n"] == 1
+    nat.reset_load_failure()
+    with pytest.raises(nat.SpectralError):
+        nat.lib()
+    assert calls["n"] == 2
+
+
+def test_output_buffers_are_validated():
+    """Caller-supplied outputs of the wrong size / dtype are refused before libspx writes through them."""
+    from sdr_iq_visualizer_b200 import spectral
+    spectral._check_buffer(np.empty((3, 8), np.float32), (3, 8), np.float32, "db_rows")
+    with pytest.raises(ValueError):
+        spectral._check_buffer(np.empty((3, 8), np.float64), (3, 8), np.float32, "db_rows")
+    with pytest.raises(ValueError):
+        spectral._check_buffer(np.empty((2, 8), np.float32), (3, 8), np.float32, "db_rows")
+    import torch
+    spectral._check_buffer(torch.empty((3, 8), dtype=torch.uint8), (3, 8), np.uint8, "wf_rows")
+    with pytest.raises(ValueError):
+        spectral._check_buffer(torch.empty((3, 8), dtype=torch.float64), (3, 8), np.float32, "maxhold")

@@ -51,14 +51,15 @@ def run_emul(lib, x, nfft, hop, kind, fmt=0, scale=1.0, tw_mode=0, n_streams=1, 
                            _p(out["wf"]), _p(out["spec"]), _p(out["welch"]), _p(out["maxhold"]))
     assert rc == 0
     out["F"] = F
-    out["win32"] = w
+    out["win64"] = None if w is None else sref.window(kind, nfft) * scale
     return out
 
 
-def oracle_power(x, nfft, hop, w32, fmt=0, n_streams=1):
-    """float64 oracle evaluated on exactly what the kernel sees: the float32-rounded window."""
+def oracle_power(x, nfft, hop, win64, fmt=0, n_streams=1):
+    """float64 oracle with the float64 window of the reference (np.hanning via mlab, process_sigmf_data.py:188); the
+    kernel's float32 window table is NOT fed back into the oracle."""
     xs = sref.as_complex128(x, fmt).reshape(n_streams, -1)
-    w = np.ones(nfft) if w32 is None else w32.astype(np.float64)
+    w = np.ones(nfft) if win64 is None else win64
     rows = []
     for s in range(n_streams):
         fr = sref.frames(xs[s], nfft, hop)
@@ -83,7 +84,7 @@ def test_emul_cf32_parity(emul, nfft, hop, kind):
     L = nfft + hop * 7 + 5  # ragged tail is dropped
     x = sref.synth_iq(L, seed=nfft + 1).astype(np.complex64)
     o = run_emul(emul, x, nfft, hop, kind)
-    X = oracle_power(x, nfft, hop, o["win32"])
+    X = oracle_power(x, nfft, hop, o["win64"])
     P = X.real**2 + X.imag**2
     assert o["F"] == 8
     got = o["spec"][..., 0] + 1j * o["spec"][..., 1]
@@ -108,7 +109,7 @@ def test_emul_ci16_and_scale(emul):
     x = sref.to_ci16(sref.synth_iq(n + 9 * hop, seed=2))
     for scale in (1.0, 2.0**-15):
         o = run_emul(emul, x, n, hop, "hann", fmt=1, scale=scale, vmin=-40.0, vmax=120.0)
-        X = oracle_power(x, n, hop, o["win32"], fmt=1)
+        X = oracle_power(x, n, hop, o["win64"], fmt=1)
         P = X.real**2 + X.imag**2
         parity.check_db_rows(o["db"], P, what=f"ci16 scale={scale}")
         parity.check_power(o["welch"][0], P.sum(axis=0), what="welch")
@@ -119,7 +120,7 @@ def test_emul_register_twiddles_match_table(emul):
     x = sref.synth_iq(n + 3 * hop, seed=4).astype(np.complex64)
     a = run_emul(emul, x, n, hop, "hann", tw_mode=0)
     b = run_emul(emul, x, n, hop, "hann", tw_mode=1)
-    X = oracle_power(x, n, hop, a["win32"])
+    X = oracle_power(x, n, hop, a["win64"])
     P = X.real**2 + X.imag**2
     parity.check_db_rows(b["db"], P, what="TW_REG")
     assert np.abs(a["spec"] - b["spec"]).max() <= 2e-6 * np.sqrt(P.mean())
@@ -145,7 +146,7 @@ def test_emul_multistream_chunking(emul):
     xs = np.concatenate([sref.synth_iq(L, seed=10 + s, snr_db=5 * (s + 1)) for s in range(S)]).astype(np.complex64)
     for fpc in (1, 4, 11, 64):
         o = run_emul(emul, xs, n, hop, "hann", n_streams=S, fpc=fpc)
-        X = oracle_power(xs, n, hop, o["win32"], n_streams=S)
+        X = oracle_power(xs, n, hop, o["win64"], n_streams=S)
         P = (X.real**2 + X.imag**2).reshape(S, -1, n)
         for s in range(S):
             parity.check_power(o["welch"][s], P[s].sum(axis=0), what=f"welch s={s} fpc={fpc}")

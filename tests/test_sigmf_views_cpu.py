@@ -106,5 +106,5 @@ def test_streamer_peek_does_not_consume():
     assert s.peek_latest() is None
     s._push({"i": 1}); s._push({"i": 2})
     assert s.peek_latest() == {"i": 2} and s.data_queue.qsize() == 2
-    assert s.get_latest_data() == {"i": 2} and s.peek_latest() == {"i": 2}
+    assert s.get_latest_data() == {"i": 1} and s.peek_latest() == {"i": 2}
     assert views.classify_tool_text(None) == {"stats": "No SDR data available yet. Please start streaming.", "include_graph": None}

@@ -19,9 +19,7 @@ def sp():
 
 def oracle_rows(x, nfft, hop, kind, fmt=0, scale=1.0, n_streams=1):
     xs = sref.as_complex128(x, fmt).reshape(n_streams, -1)
-    w = sref.window(kind, nfft)
-    if sref.window_id(kind) != 0 or scale != 1.0:
-        w = (w * scale).astype(np.float32).astype(np.float64)  # the kernel's float32 table
+    w = sref.window(kind, nfft) * scale   # float64 window, as the reference's np.hanning (process_sigmf_data.py:188)
     out = []
     for s in range(n_streams):
         fr = sref.frames(xs[s], nfft, hop)
@@ -231,7 +229,7 @@ def test_config2_slice_and_full_size_properties(sp):
     rf = pl.stft(full, welch=True, maxhold=True)
     assert rf.n_frames == 59_997
     # Parseval per frame summed over frames: sum_k sum_f |X_f[k]|^2 = N * sum_f sum_n |w[n] x_f[n]|^2
-    w = sref.window("hann", n).astype(np.float32).astype(np.float64)
+    w = sref.window("hann", n)   # float64 window (the kernel's float32 table differs by <= 6e-8 relative: inside 1e-6)
     iq = full.reshape(-1, 2).astype(np.float64)
     e = iq[:, 0] ** 2 + iq[:, 1] ** 2
     # sum over frames of sum_n w^2[n] e[f*hop+n]  via correlation of e with w^2 at stride hop
