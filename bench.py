@@ -7,18 +7,25 @@ uint8 waterfall rows, the Welch sum, the max-hold and the classifier features of
 One "step" = one pass of that path over that batch.
 
   value   : whole-job Msamples/s with the input already resident in HBM (device buffers).
-  e2e     : the same step through the host-buffer C-ABI call (pinned host input and outputs;
-            H2D of the samples and D2H of rows/PSD inside the timed region).
-  roofline: the fused STFT kernel's algorithmic bytes (8 B/sample: 4 in + 4 x 1 B rows) over its
-            CUDA-event duration vs the measured HBM peak; FP32 issue figures alongside because this
-            shape is instruction-bound, not HBM-bound.
+  e2e     : the same step through the pinned ingest ring of the C ABI (spx_ring_*: config 2 IS the ring-buffer
+            stream): per 2^22-sample slot H2D -> fused STFT -> D2H of rows / Welch / max-hold / features, all inside
+            the timed region; the producer writes in place (the slots are the DMA target).  The one-shot host-buffer
+            call (spx_stft_exec, SPX_MEM_HOST) and the box's raw concurrent-copy ceiling are measured beside it.
+  roofline: this shape transforms every sample four times, so FP32 binds: achieved nominal TFLOP/s
+            (5 N log2 N + 20 N per frame) over the CUDA-event duration of the fused STFT kernel vs the FP32 FMA peak
+            measured in the same run; the HBM fraction (8 B/sample) and the HBM-bound headline shape are alongside.
+  sustained: the same device-resident step looped for >= 2 s with NVML clock / power samples.
+  sharded : the configs that shard, strong scaling over the ranks of this run, parity-checked in
+            the same run: config 5 (2^30-sample capture, 65536-pt, fused peer reduction; rows sharded or gathered
+            to rank 0, NCCL all-reduce + gather as the baseline) and config 4 (64 streams x 2^24).
   cpu_baseline: the float64 numpy oracle (a port: the reference has no windowed/overlapped path)
             on a bounded slice, single core, timed on this box.
 
 `--impl reference` times the CPU oracle port with all host cores (multiprocessing over frame
 blocks) on the same config and prints the same line with "impl": "reference".
-Multi-GPU: config 2 is one ordered stream, so ranks are independent replicas (one stream per GPU,
-no data-path collective); torch.distributed is used only for the barrier and the max-over-ranks.
+Multi-GPU: config 2 is one ordered stream, so for `value` / `e2e` the ranks are independent replicas (one stream per
+GPU, no data-path collective); the `sharded` block carries the configs with a real exchange step.
+torch.distributed is the plumbing (barriers, IPC handles, tiny tensors).
 """
 import argparse
 import json
@@ -63,7 +70,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.sm, self.mask, self.max_mhz, self.power = [], 0, None, []
         self._stop = threading.Event()
         self._thr = None
         self._nvml = None
@@ -104,6 +111,7 @@ class ClockSampler:
                     nv, h = self._nvml
                     self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                     self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
                 else:
                     self._sample_smi()
             except Exception:
@@ -116,7 +124,9 @@ class ClockSampler:
             self._thr.join(timeout=15)
         reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-                "reasons": reasons, "samples": len(self.sm), "source": "nvml" if self._nvml else "nvidia-smi"}
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml" if self._nvml else "nvidia-smi",
+                "power_w_max": round(max(self.power), 1) if self.power else None,
+                "sm_mhz_min": float(min(self.sm)) if self.sm else None}
 
 
 def dist_setup(n_gpus):
@@ -185,6 +195,56 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def numa_info(nat, local):
+    """Where this rank's CPU threads and its GPU sit (the pinned buffers are first-touched after the affinity call)."""
+    info = {}
+    try:
+        import pynvml
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            info["gpu_numa_node"] = int(fh.read().strip())
+    except Exception:
+        info["gpu_numa_node"] = None
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        info["cpu_affinity"] = f"{len(cpus)} cpus [{cpus[0]}..{cpus[-1]}]"
+        nodes = set()
+        for nd in os.listdir("/sys/devices/system/node"):
+            if nd.startswith("node"):
+                with open(f"/sys/devices/system/node/{nd}/cpulist") as fh:
+                    rng = fh.read().strip()
+                members = set()
+                for part in rng.split(","):
+                    if part:
+                        a, _, b = part.partition("-")
+                        members.update(range(int(a), int(b or a) + 1))
+                if members & set(cpus):
+                    nodes.add(int(nd[4:]))
+        info["cpu_numa_nodes"] = sorted(nodes)
+    except Exception:
+        pass
+    return info
+
+
+def traffic_record(kernel_name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture; refused (None) unless the capture
+    names the kernel this run launched."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        if t.get("kernel") != kernel_name:
+            return None, f"profiles/traffic.json is for {t.get('kernel')!r}, this run launched {kernel_name!r}"
+        return t.get("c2_stft_kernel_dram_bytes_per_launch"), f"{t.get('source')} (ncu --set full, commit {t.get('git_sha')})"
+    except Exception as exc:
+        return None, f"no traffic record: {exc}"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +253,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("SPX_VARIANT", "-1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the config-4 / config-5 strong-scaling block")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sharded-log2", type=int, default=30, help="config-5 capture length (2^30 is BASELINE's size)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -209,10 +272,11 @@ def main():
     except Exception:
         pass
     from sdr_iq_visualizer_b200 import _native as nat
-    from sdr_iq_visualizer_b200 import features, spectral as sp
+    from sdr_iq_visualizer_b200 import features, ring as ringmod, spectral as sp
     nat.require_device()
     dev = local
     peaks, peak_src = measured_peaks()
+    numa = numa_info(nat, local)
 
     host_in = nat.pinned_empty(2 * L_STEP, np.int16)
     host_in[:] = synth_ci16(L_STEP, seed=2 + rank)
@@ -227,6 +291,7 @@ def main():
     d_mh = nat.DeviceArray((1, NFFT), np.float32, dev)
     d_pxx = nat.DeviceArray((NFFT,), np.float64, dev)
     d_pdb = nat.DeviceArray((NFFT,), np.float64, dev)
+    d_we_flat = nat.DeviceView(d_we.ptr, (NFFT,), np.float64, dev)
     st = pl.stream
     total_timer = nat.DeviceTimer(dev, st)
     kernel_timers = [nat.DeviceTimer(dev, st) for _ in range(args.steps)]
@@ -238,7 +303,7 @@ def main():
         res = pl.stft(d_in, wf_rows=d_wf, welch=d_we, maxhold=d_mh, vmin=VMIN, vmax=VMAX)
         if ktimer is not None:
             ktimer.stop()
-        pl.welch_finalize(d_we, res.n_frames, FS, pxx=d_pxx, pdb=d_pdb)
+        pl.welch_finalize(d_we_flat, res.n_frames, FS, pxx=d_pxx, pdb=d_pdb)
         # classifier features of this Welch block: kernel + asynchronous copy of the result struct to pinned memory,
         # everything enqueued on the plan's stream (the host never waits inside a step; results are read after the loop)
         return fq.enqueue(d_pdb, NFFT)
@@ -261,11 +326,81 @@ def main():
     kernel_ms = [t.elapsed_ms() for t in kernel_timers]
     dt_dev = barrier_max(dist, local, dt_dev)
 
-    # ---------------- end-to-end leg: host (pinned) buffers through the C ABI, copies inside the timed region
+    # ---------------- sustained leg: the same step back to back for >= 2 s (a 13 ms burst cannot show a power / thermal
+    # limit); its own clock / power samples
+    sustained = None
+    if not args.no_sustained:
+        n_sus = int(min(20000, max(args.steps, 2.2 / max(dt_dev / args.steps, 1e-5))))
+        sus_sampler = ClockSampler(dev)
+        sus_timer = nat.DeviceTimer(dev, st)
+        if dist is not None:
+            dist.barrier()
+        nat.device_sync(dev)
+        sus_sampler.start()
+        sus_timer.start()
+        for _ in range(n_sus):
+            device_step(None)
+        sus_timer.stop()
+        dt_sus = sus_timer.elapsed_ms() * 1e-3
+        nat.device_sync(dev)
+        sus_clocks = sus_sampler.stop()
+        dt_sus = barrier_max(dist, local, dt_sus)
+        sustained = {"steps": n_sus, "seconds": round(dt_sus, 3), "value": round(world * L_STEP * n_sus / dt_sus / 1e6, 1),
+                     "unit": "Msamples/s", "ms_per_step": round(dt_sus / n_sus * 1e3, 4), "clocks": sus_clocks,
+                     "vs_burst": round((L_STEP * n_sus / dt_sus) / (L_STEP * args.steps / dt_dev), 4)}
+
+    # ---------------- end-to-end leg 1: the pinned ingest ring (config 2 is the ring-buffer stream).  Per slot:
+    # H2D of 2^22 samples -> fused STFT (+ Welch finalize + classifier features) -> D2H of the slot's rows, Welch sum,
+    # max-hold, PSD and feature struct.  In-place producer: the pinned slots are where the radio DMA would land, so the
+    # timed loop commits them without rewriting their contents (filled once, untimed, below).
+    SLOT = 1 << 22
+    n_full, tail = divmod(L_STEP, SLOT)
+    slot_sizes = [SLOT] * n_full + ([tail] if tail else [])
+    rg = ringmod.StreamRing(pl, n_slots=4, slot_samples=SLOT, wf_rows=True, welch=True, maxhold=True, vmin=VMIN, vmax=VMAX,
+                            features=True, sample_rate=FS)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def ring_pass(fill):
+        """One step = one second of the stream through the ring; returns the feature dict of the last block."""
+        pending, pos, last = 0, 0, None
+        for n in slot_sizes:
+            buf = rg.acquire()
+            if fill:
+                buf[: 2 * n] = host_in[2 * pos: 2 * (pos + n)]      # memcpy producer (warm-up / comparison only)
+            rg.commit(n)
+            pos += n
+            pending += 1
+            if pending >= 3:
+                last = rg.collect(); rg.release(); pending -= 1
+        while pending:
+            last = rg.collect(); rg.release(); pending -= 1
+        return last
+
+    t0 = time.perf_counter()
+    ring_pass(True)
+    dt_fill = time.perf_counter() - t0          # same pass with a single-threaded numpy memcpy producer, for the record
+    ring_pass(False)
+    st0 = rg.stats()
+    if dist is not None:
+        dist.barrier()
+    nat.device_sync(dev)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        blk = ring_pass(False)
+    nat.device_sync(dev)
+    dt_ring_local = time.perf_counter() - t0
+    st1 = rg.stats()
+    dt_ring = barrier_max(dist, local, dt_ring_local)
+    ring_h2d = (st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps
+    ring_d2h = (st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps
+    feat_ring = blk["features"]
+    rg.close()
+
+    # ---------------- end-to-end leg 2: the one-shot host-buffer call (spx_stft_exec with SPX_MEM_HOST)
     h_wf = nat.pinned_empty((F, NFFT), np.uint8)
     h_we = nat.pinned_empty((1, NFFT), np.float64)
     h_mh = nat.pinned_empty((1, NFFT), np.float32)
-    e2e_steps = max(3, min(args.steps, 10))
+    call_steps = 3
 
     def e2e_step():
         r = pl.stft(host_in, wf_rows=h_wf, welch=h_we, maxhold=h_mh, vmin=VMIN, vmax=VMAX)
@@ -278,14 +413,45 @@ def main():
         dist.barrier()
     nat.device_sync(dev)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(call_steps):
         r, feat_h = e2e_step()
     nat.device_sync(dev)
-    dt_e2e_local = time.perf_counter() - t0
-    clocks = sampler.stop()     # sampled through both timed regions (device-resident leg and end-to-end leg)
-    dt_e2e = barrier_max(dist, local, dt_e2e_local)
-    h2d = r.h2d_bytes + NFFT * 8
-    d2h = r.d2h_bytes + NFFT * 8 + 160
+    dt_call = barrier_max(dist, local, time.perf_counter() - t0)
+    clocks = sampler.stop()     # sampled through the device-resident leg and both end-to-end legs
+
+    # ---------------- the box's raw copy ceiling for exactly these bytes: the same pinned buffers, H2D and D2H at once on
+    # two streams in 16 MiB pieces, nothing else running; every rank copies at the same time (as in the e2e legs)
+    ceil_s = None
+    try:
+        import ctypes as C
+        sec = C.c_double()
+        if dist is not None:
+            dist.barrier()
+        nat.check(nat.lib().spx_copy_ceiling(dev, host_in.ctypes.data, host_in.nbytes, h_wf.ctypes.data, h_wf.nbytes,
+                                             16 << 20, 3, C.byref(sec)))
+        ceil_s = barrier_max(dist, local, float(sec.value))
+    except Exception as exc:   # reported, never fatal
+        print(f"copy ceiling probe failed: {exc}", file=sys.stderr)
+
+    # ---------------- sharded configs (strong scaling over the ranks of this run), parity-checked in the same run
+    sharded = None
+    if not args.no_sharded:
+        # free what the config-2 legs held before the 8 GiB captures are allocated
+        pl.close(); d_in.free(); d_wf.free()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_sharded as bs
+        ctx = bs.Ctx(rank, world, local, dist)
+        block = bs.synth_block()
+        lg = args.sharded_log2
+        sharded = {"scaling": "strong", "n_gpus": world, "unit": "Msamples/s",
+                   "c5": {"workload": f"config5: 2^{lg} cf32 samples, 65536-pt Hann, 50% overlap, u8 rows + Welch + max-hold; "
+                                      "frame blocks with (N - hop)-sample halos per rank",
+                          "reduce_only": bs.run_c5(ctx, "fused", "sharded", lg, 5, 2, True, block),
+                          "gather_to_rank0": bs.run_c5(ctx, "fused", "gather", lg, 5, 2, True, block),
+                          "nccl_allreduce_gather": bs.run_c5(ctx, "nccl", "gather", lg, 3, 2, True, block, measure_kernel=False)},
+                   "c4": dict(bs.run_c4(ctx, 24, 64, 5, 2, True, block),
+                              workload="config4: 64 streams x 2^24 cf32, 2048-pt Hann, 50% overlap, per-stream Welch PSD + classifier "
+                                       "features; contiguous blocks of streams per rank")}
 
     if rank != 0:
         if dist is not None:
@@ -311,13 +477,28 @@ def main():
     plh.close(); d_xh.free(); d_dbh.free()
 
     k_ms = float(np.mean(kernel_ms))
-    achieved = L_STEP * BYTES_PER_SAMPLE / (k_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get("c2_stft_kernel_dram_bytes_per_launch")
-    except Exception:
-        pass
+    achieved_gbs = L_STEP * BYTES_PER_SAMPLE / (k_ms * 1e-3) / 1e9
+    achieved_tf = L_STEP * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12
+    kernel_name = f"stft_kernel<4096,ci16,acc> variant {variant}"
+    traffic, traffic_src = traffic_record(kernel_name)
+    ring_gsps = world * L_STEP * e2e_steps / dt_ring
+    e2e = {"value": round(ring_gsps / 1e6, 1), "unit": "Msamples/s",
+           "h2d_bytes_per_step": int(ring_h2d), "d2h_bytes_per_step": int(ring_d2h), "steps": e2e_steps,
+           "ms_per_step": round(dt_ring / e2e_steps * 1e3, 3),
+           "h2d_gbs_per_gpu": round(ring_h2d * e2e_steps / dt_ring / 1e9, 2), "d2h_gbs_per_gpu": round(ring_d2h * e2e_steps / dt_ring / 1e9, 2),
+           "path": "spx_ring_* (pinned ring, 4 slots x 2^22 samples): per slot H2D -> fused STFT + Welch finalize + classifier "
+                   "features -> D2H of rows / Welch / max-hold / PSD / features; in-place producer (slots are the DMA target)",
+           "memcpy_producer_first_pass_ms": round(dt_fill * 1e3, 1),
+           "one_shot_call": {"value": round(world * L_STEP * call_steps / dt_call / 1e6, 1), "ms_per_step": round(dt_call / call_steps * 1e3, 3),
+                             "h2d_bytes_per_step": int(r.h2d_bytes + NFFT * 8), "d2h_bytes_per_step": int(r.d2h_bytes + NFFT * 8 + 160),
+                             "path": "spx_stft_exec(SPX_MEM_HOST) on the whole second + spx_welch_finalize + spx_classify_features"},
+           "numa": numa}
+    if ceil_s:
+        e2e["copy_ceiling"] = {"ms_per_step": round(ceil_s * 1e3, 3), "h2d_gbs_per_gpu": round(host_in.nbytes / ceil_s / 1e9, 2),
+                               "d2h_gbs_per_gpu": round(h_wf.nbytes / ceil_s / 1e9, 2),
+                               "how": "spx_copy_ceiling: the same pinned buffers, H2D + D2H at once, 16 MiB pieces, all ranks at once, max over ranks"}
+        e2e["frac_of_copy_ceiling"] = round(ceil_s / (dt_ring / e2e_steps), 4)
+        e2e["one_shot_call"]["frac_of_copy_ceiling"] = round(ceil_s / (dt_call / call_steps), 4)
     line = {
         "metric": METRIC, "value": round(world * L_STEP * args.steps / dt_dev / 1e6, 1), "unit": "Msamples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt_dev / args.steps * 1e3, 4),
@@ -328,26 +509,30 @@ def main():
                    "l2": "step input (246 MB) + rows (246 MB) exceed the 126 MB L2; no explicit flush",
                    "timing": "CUDA events on the plan's compute stream around the K steps (max over ranks); "
                              "the STFT kernel additionally bracketed per launch",
-                   "multi_gpu": "replicas only: one independent stream per GPU, no data-path collective",
+                   "multi_gpu": "value / e2e: replicas only (one independent stream per GPU, no data-path collective); "
+                                "the configs that shard are in `sharded` (strong scaling, fused peer reduction)",
                    "real_time_margin_x": round(L_STEP * args.steps / dt_dev / FS, 1)},
-        "e2e": {"value": round(world * L_STEP * e2e_steps / dt_e2e / 1e6, 1), "unit": "Msamples/s",
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                "ms_per_step": round(dt_e2e / e2e_steps * 1e3, 3),
-                "h2d_gbs": round(h2d * e2e_steps / dt_e2e / 1e9, 2), "d2h_gbs": round(d2h * e2e_steps / dt_e2e / 1e9, 2)},
+        "e2e": e2e,
         "gpu_launches": 3 * args.steps,
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "stft_kernel<4096,ci16,acc>", "kernel_ms": round(k_ms, 4),
-                     "bytes_per_sample": BYTES_PER_SAMPLE, "kernel_share_of_step": round(k_ms * args.steps / (dt_dev * 1e3), 3),
-                     "fp32_tflops_nominal": round(L_STEP * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12, 2),
-                     "fp32_peak_tflops_measured": round(p32, 2),
-                     "frac_of_fp32_peak_nominal_flops": round(L_STEP * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12 / p32, 4),
+        "roofline": {"bound": "fp32", "achieved": round(achieved_tf, 2), "peak": round(p32, 2), "unit": "TFLOP/s",
+                     "frac": round(achieved_tf / p32, 4), "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": "FP32 FMA micro-kernel measured in this run (MEASURED_PEAKS.json holds no FP32 figure)",
+                     "flop_per_sample": FLOP_PER_SAMPLE,
+                     "kernel": kernel_name, "kernel_ms": round(k_ms, 4),
+                     "kernel_share_of_step": round(k_ms * args.steps / (dt_dev * 1e3), 3),
+                     "hbm": {"achieved_gbs": round(achieved_gbs, 1), "peak_gbs": peaks["hbm_gbs"], "frac": round(achieved_gbs / peaks["hbm_gbs"], 4),
+                             "bytes_per_sample": BYTES_PER_SAMPLE, "peak_source": peak_src},
                      "note": "this shape transforms every sample 4 times (75% overlap): 320 nominal flop/sample vs 8 B/sample, "
-                             "so FP32 issue binds before HBM (SURVEY 8d); the HBM-bound shape of north_star is in headline_shape",
+                             "so FP32 binds before HBM (SURVEY 8d); the HBM-bound shape of north_star is in headline_shape",
                      "headline_shape": headline},
         "clocks": clocks,
-        "features": {"snr_db": round(feat["snr_db"], 2), "peak_count": feat["peak_count"]},
+        "features": {"snr_db": round(feat["snr_db"], 2), "peak_count": feat["peak_count"],
+                     "ring_snr_db": None if not feat_ring else round(feat_ring["snr_db"], 2)},
     }
+    if sustained is not None:
+        line["sustained"] = sustained
+    if sharded is not None:
+        line["sharded"] = sharded
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single()
     print(json.dumps(line), flush=True)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SPX_ABI_VERSION 2
+#define SPX_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SPX_API __attribute__((visibility("default")))
@@ -98,6 +98,16 @@ SPX_API int spx_memcpy_d2h(int device, void* dst, const void* src, size_t bytes)
 SPX_API int spx_memcpy_d2h_async(int device, void* dst_host, const void* src, size_t bytes, void* stream);
 SPX_API int spx_memset(int device, void* dst, int value, size_t bytes);
 SPX_API int spx_device_sync(int device);
+/* device -> device copy on `stream`; either pointer may be a peer GPU's buffer mapped with spx_ipc_open (NVLink) */
+SPX_API int spx_memcpy_d2d_async(int device, void* dst, const void* src, size_t bytes, void* stream);
+SPX_API int spx_stream_sync(int device, void* stream);
+
+/* Measured copy ceiling of THIS box for the end-to-end path: h2d_bytes from `host_in` and d2h_bytes into `host_out`
+ * (the caller's own pinned buffers) move concurrently on two streams in `piece_bytes` pieces, nothing else running;
+ * seconds_out = wall time per repetition (mean of `iters` after one warm-up).  bench.py prints the end-to-end step
+ * time against it (e2e.frac_of_copy_ceiling), per rank and with all ranks copying at once. */
+SPX_API int spx_copy_ceiling(int device, const void* host_in, size_t h2d_bytes, void* host_out, size_t d2h_bytes,
+                             size_t piece_bytes, int iters, double* seconds_out);
 
 /* ---------------------------------------------------------------- peer memory (one process per GPU)
  * The multi-GPU configs reduce partial Welch sums / max-holds and collect waterfall rows on one rank
@@ -108,6 +118,31 @@ SPX_API int spx_device_sync(int device);
 SPX_API int spx_ipc_export(int device, void* dptr, void* handle_out);
 SPX_API int spx_ipc_open(int device, const void* handle, void** dptr_out);
 SPX_API int spx_ipc_close(int device, void* dptr);
+
+/* The collective step of a sharded capture (the reference is single-process, app/sdr/streamer.py:58),
+ * for consumers that do not go through Python:
+ *   spx_peer_reduce     adds this GPU's partial Welch sums (float64) / max-holds (float32, MAX) into the owner's
+ *                       mapped buffers with system-scope atomics over NVLink (n = n_streams * nfft elements);
+ *   spx_peer_push_rows  copy-engine push of a block of finished uint8 rows into the owner's mapped row buffer. */
+SPX_API int spx_peer_reduce(int device, const double* welch_local, const float* maxhold_local, double* welch_owner,
+                            float* maxhold_owner, int64_t n, void* stream);
+SPX_API int spx_peer_push_rows(int device, void* rows_owner, const void* rows_local, size_t bytes, void* stream);
+
+/* The same step over NCCL (libnccl.so.2 is loaded with dlopen at first use; SPX_NCCL_LIB overrides the path):
+ *   spx_nccl_unique_id  rank 0 creates the 128-byte id and hands it to the other ranks out of band;
+ *   spx_nccl_init       one communicator per process / GPU;
+ *   spx_allreduce_welch in place: welch_acc SUM (float64[n]), maxhold MAX (float32[n]), *n_frames_inout SUM
+ *                       (any of the three may be NULL); with n_frames_inout it waits for `stream`;
+ *   spx_gather_rows     uint8 rows of every rank, in rank order, into rows_all on rank dst (bytes_per_rank[nranks]). */
+typedef struct spx_comm spx_comm;
+#define SPX_NCCL_ID_BYTES 128
+SPX_API int spx_nccl_unique_id(void* id_out_128);
+SPX_API int spx_nccl_init(spx_comm** out, int device, int rank, int nranks, const void* unique_id_128);
+SPX_API int spx_nccl_destroy(spx_comm* comm);
+SPX_API int spx_allreduce_welch(spx_comm* comm, double* welch_acc, float* maxhold, int64_t n, int64_t* n_frames_inout,
+                                void* stream);
+SPX_API int spx_gather_rows(spx_comm* comm, const void* rows_local, int64_t local_bytes, void* rows_all,
+                            const int64_t* bytes_per_rank, int dst, void* stream);
 
 /* ---------------------------------------------------------------- STFT plan */
 typedef struct spx_plan spx_plan;

@@ -139,6 +139,17 @@ _SIGNATURES = {
     "spx_ipc_export": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "spx_ipc_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "spx_ipc_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "spx_memcpy_d2d_async": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "spx_stream_sync": (C.c_int, [C.c_int, C.c_void_p]),
+    "spx_copy_ceiling": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                   C.POINTER(C.c_double)]),
+    "spx_peer_reduce": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "spx_peer_push_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "spx_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "spx_nccl_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "spx_nccl_destroy": (C.c_int, [C.c_void_p]),
+    "spx_allreduce_welch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "spx_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
     "spx_timer_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "spx_timer_start": (C.c_int, [C.c_void_p, C.c_void_p]),
     "spx_timer_stop": (C.c_int, [C.c_void_p, C.c_void_p]),

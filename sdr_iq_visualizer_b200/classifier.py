@@ -44,7 +44,7 @@ def measure(freqs, power_db) -> dict:
     m["bw3"] = _span(freqs, m["first_3db"], m["last_3db"])
     m["bw10"] = _span(freqs, m["first_10db"], m["last_10db"])
     m["bw20"] = _span(freqs, m["first_20db"], m["last_20db"])
-    m["peak_spacing_std_hz"] = _spacing_std(freqs, m["peaks"]) if m["peak_count"] == len(m["peaks"]) else 0.0
+    m["peak_spacing_std_hz"] = _spacing_std(freqs, m["peaks"])   # the list is complete (features.measure_batch raises otherwise)
     return m
 
 
@@ -230,7 +230,10 @@ def _spectral_kurtosis(power_db):
 def _find_peaks(power_db, threshold_db, min_distance_bins=5):
     if len(power_db) < 3:
         return []
-    m = _features.measure(power_db, peak_threshold_db=float(threshold_db), min_distance_bins=int(min_distance_bins))
+    # reference loop (classifier.py:200-212): a distance <= 0 keeps EVERY strict local maximum, exactly like 1 or 2
+    # (strict maxima are never adjacent); the kernel reads 0 as "use max(3, n//300)", so pass 1 for those
+    md = int(min_distance_bins)
+    m = _features.measure(power_db, peak_threshold_db=float(threshold_db), min_distance_bins=md if md >= 1 else 1)
     return list(m["peaks"])
 
 

@@ -15,6 +15,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "spx_plan.h"
 #include "spx_stft_kernel.cuh"
 #include "spx_tables.h"
@@ -22,6 +24,9 @@
 namespace spx {
 
 static thread_local char g_err[512] = "";
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 int spx_set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -184,8 +189,11 @@ static int stft_exec_host(spx_plan* pl, spx_stft_args* a, long long F) {
             if (left <= piece) step = left > piece / 4 ? (left + 1) / 2 : left;
             if (step < (long long)N) step = (long long)N;
             const long long hi = lo + step < L ? lo + step : L;
-            SPX_CUDA(cudaMemcpyAsync(dd + (size_t)lo * elt, h_in + (size_t)lo * elt, (size_t)(hi - lo) * elt,
-                                     cudaMemcpyHostToDevice, pl->s_h2d));
+            {
+                NvtxRange r("spx H2D piece");
+                SPX_CUDA(cudaMemcpyAsync(dd + (size_t)lo * elt, h_in + (size_t)lo * elt, (size_t)(hi - lo) * elt,
+                                         cudaMemcpyHostToDevice, pl->s_h2d));
+            }
             h2d += (hi - lo) * (long long)elt;
             long long f_hi = spx_frame_count(hi, N, hop);
             if (hi == L) f_hi = F;
@@ -196,6 +204,7 @@ static int stft_exec_host(spx_plan* pl, spx_stft_args* a, long long F) {
             SPX_CUDA(cudaEventRecord(e_in, pl->s_h2d));
             SPX_CUDA(cudaStreamWaitEvent(pl->s_compute, e_in, 0));
             const size_t r0 = (size_t)(s * F + f_lo);
+            NvtxRange r_k("spx STFT kernel piece");
             SPX_TRY(stft_launch_device(pl, dd + (size_t)(f_lo * hop) * elt, 1, 0, f_hi - f_lo,
                                        d_db ? d_db + r0 * N : nullptr, d_wf ? d_wf + r0 * N : nullptr,
                                        d_spec ? d_spec + r0 * N : nullptr, d_welch ? d_welch + s * N : nullptr,
@@ -206,6 +215,7 @@ static int stft_exec_host(spx_plan* pl, spx_stft_args* a, long long F) {
         }
     }
     // drain rows as their kernels finish
+    NvtxRange r_d2h("spx D2H rows");
     size_t evi = 1;
     for (const Piece& pc : pieces) {
         cudaEvent_t e_k = pl->events[evi];
@@ -254,6 +264,13 @@ __global__ void peer_reduce_kernel(const double* __restrict__ w_local, const flo
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         flush_acc(w_local ? w_peer : nullptr, m_local ? m_peer : nullptr, i, 0.f, 0.f, -1, w_local ? w_local[i] : 0.0,
                   m_local ? m_local[i] : 0.f);
+}
+
+int peer_reduce_launch(const double* w_local, const float* m_local, double* w_peer, float* m_peer, long long n, cudaStream_t st) {
+    if (n <= 0 || (!w_local && !m_local)) return SPX_OK;
+    peer_reduce_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(w_local, m_local, w_peer, m_peer, n);
+    SPX_CUDA(cudaGetLastError());
+    return SPX_OK;
 }
 
 static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cudaStream_t st) {
@@ -313,10 +330,8 @@ static int stft_exec_device_peer(spx_plan* pl, spx_stft_args* a, long long F, cu
         }
     }
     if (w_local || m_local) {
-        const long long n = S * N;
-        peer_reduce_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(w_local, m_local, a->welch_acc,
-                                                                                                     a->maxhold, n);
-        SPX_CUDA(cudaGetLastError());
+        NvtxRange r("spx peer reduce (system-scope atomics over NVLink)");
+        SPX_TRY(peer_reduce_launch(w_local, m_local, a->welch_acc, a->maxhold, S * N, st));
     }
     // whoever waits on `st` (spx_plan_sync, a later launch) also waits for the last copies
     if (a->wf_rows && !rows_local) {

@@ -18,6 +18,15 @@ int spx_set_error(int code, const char* fmt, ...);
                                         __FILE__, __LINE__);                                             \
     } while (0)
 
+// NVTX range (tracing row): names the H2D / kernel / D2H enqueue sections of the host pipeline, the
+// ingest ring and the peer-output path in nsys / ncu timelines.  Header-only NVTX3: a no-op unless a tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 #define SPX_TRY(expr)                 \
     do {                              \
         int _rc = (expr);             \

@@ -55,6 +55,7 @@ int bigfft_plan_init(spx_plan* pl);
 int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,
                          unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
                          float vmax, cudaStream_t st, int sys_atomics = 0);
+int peer_reduce_launch(const double* w_local, const float* m_local, double* w_peer, float* m_peer, long long n, cudaStream_t st);
 int welch_finalize_launch(const double* acc, int n, double inv_norm, double* pxx, double* pxx_db, cudaStream_t st);
 int bluestein_plan_init(spx_plan* pl);
 int bluestein_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,

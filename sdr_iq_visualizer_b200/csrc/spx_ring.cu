@@ -165,6 +165,7 @@ extern "C" int spx_ring_commit(spx_ring* r, int64_t n_samples) {
     const int N = pl->cfg.nfft, hop = pl->cfg.hop;
     const size_t elt = r->elt;
     const long long carry = r->carry;
+    NvtxRange r_commit("spx ring commit: H2D -> STFT -> D2H");
     // H2D of the new samples behind the carried tail
     if (n_samples) SPX_CUDA(cudaMemcpyAsync(s.d_in + (size_t)carry * elt, s.h_in, (size_t)n_samples * elt, cudaMemcpyHostToDevice, pl->s_h2d));
     SPX_CUDA(cudaEventRecord(s.e_h2d, pl->s_h2d));

@@ -58,7 +58,10 @@ def measure_batch(power_db, n: Optional[int] = None, batch: Optional[int] = None
     if batch == 0:
         return []
     out = (nat.spx_features * batch)()
-    cap = max(1, n // 3 + 2) if want_peaks else 0
+    # strict local maxima are >= 2 bins apart: at most (n+1)//2 of them survive a min distance of 1 or 2, at most
+    # n//min_dist + 1 otherwise (the default distance is max(3, n//300))
+    md = int(min_distance_bins)
+    cap = (max(1, (n + 1) // 2) if 0 < md < 3 else max(1, n // 3 + 2)) if want_peaks else 0
     peaks = np.zeros((batch, cap), np.int32) if want_peaks else None
     opts = nat.spx_feature_opts()
     opts.drop_db[0], opts.drop_db[1], opts.drop_db[2] = (float(d) for d in drops)
@@ -68,7 +71,13 @@ def measure_batch(power_db, n: Optional[int] = None, batch: Optional[int] = None
     nat.check(nat.lib().spx_classify_features(device, mem, ptr, dtype, int(n), int(batch), int(stride), out,
                                               peaks.ctypes.data if want_peaks else None, cap, C.byref(opts),
                                               stream or None))
-    return [_to_dict(out[b], peaks[b] if want_peaks else None) for b in range(batch)]
+    res = [_to_dict(out[b], peaks[b] if want_peaks else None) for b in range(batch)]
+    if want_peaks:
+        for d in res:
+            if d["peaks_stored"] != d["peak_count"]:   # cannot happen with the caps above; never hand back a cut list
+                raise nat.SpectralError(nat.E_INVALID,
+                                        f"peak list truncated: {d['peaks_stored']} of {d['peak_count']} stored")
+    return res
 
 
 def measure(power_db, device: int = 0, **opts) -> dict:

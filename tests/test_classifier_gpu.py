@@ -65,6 +65,17 @@ def test_temporal_smoothing_sequence(clf, golden_classifier):
     _clear(clf)
 
 
+@pytest.mark.parametrize("min_dist", [-3, 0, 1, 2, 3, 5])
+def test_find_peaks_small_distances_match_reference_loop(clf, min_dist):
+    """classifier.py:200-212 with min_distance_bins <= 2 keeps every strict local maximum (up to ~n/2 of them): the
+    drop-in helper must return the complete list, not the kernel's default distance and not a truncated buffer."""
+    rng = np.random.default_rng(7)
+    for n in (3, 50, 1001, 4096):
+        p = rng.normal(-80, 3, n)
+        p[1::2] += 20.0            # every odd bin is a strict local maximum: the worst case for the list size
+        assert clf._find_peaks(p, -1000.0, min_dist) == cref.greedy_peaks(cref.peak_candidates(p, -1000.0), min_dist), (n, min_dist)
+
+
 def test_reference_test_classifier_runs_unchanged(clf):
     """The reference's own tests/test_classifier.py (vendored byte for byte as tests/golden/reference_test_classifier.py,
     /root/reference/tests/test_classifier.py:1-63) executed against `app.processing.classifier` of this repo."""

@@ -23,7 +23,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libspx.so does not export {name}"
     assert declared == set(nat._SIGNATURES), declared ^ set(nat._SIGNATURES)
-    assert lib.spx_abi_version() == 2
+    assert lib.spx_abi_version() == 3
     assert lib.spx_frame_count(61_440_000, 4096, 1024) == 59_997
 
 
