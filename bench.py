@@ -360,33 +360,36 @@ def main():
                             features=True, sample_rate=FS)
     e2e_steps = max(3, min(args.steps, 10))
 
-    def ring_pass(fill):
-        """One step = one second of the stream through the ring; returns the feature dict of the last block."""
-        pending, pos, last = 0, 0, None
+    ring_state = {"pending": 0, "last": None}
+
+    def ring_pass(fill, drain):
+        """One step = one second of the stream through the ring (slots are collected two commits behind).  The stream is
+        continuous: consecutive steps keep the pipeline full, only the end of the timed region drains it."""
+        pos = 0
         for n in slot_sizes:
             buf = rg.acquire()
             if fill:
                 buf[: 2 * n] = host_in[2 * pos: 2 * (pos + n)]      # memcpy producer (warm-up / comparison only)
             rg.commit(n)
             pos += n
-            pending += 1
-            if pending >= 3:
-                last = rg.collect(); rg.release(); pending -= 1
-        while pending:
-            last = rg.collect(); rg.release(); pending -= 1
-        return last
+            ring_state["pending"] += 1
+            if ring_state["pending"] >= 3:
+                ring_state["last"] = rg.collect(); rg.release(); ring_state["pending"] -= 1
+        while drain and ring_state["pending"]:
+            ring_state["last"] = rg.collect(); rg.release(); ring_state["pending"] -= 1
+        return ring_state["last"]
 
     t0 = time.perf_counter()
-    ring_pass(True)
+    ring_pass(True, True)
     dt_fill = time.perf_counter() - t0          # same pass with a single-threaded numpy memcpy producer, for the record
-    ring_pass(False)
+    ring_pass(False, True)
     st0 = rg.stats()
     if dist is not None:
         dist.barrier()
     nat.device_sync(dev)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        blk = ring_pass(False)
+    for i in range(e2e_steps):
+        blk = ring_pass(False, i == e2e_steps - 1)
     nat.device_sync(dev)
     dt_ring_local = time.perf_counter() - t0
     st1 = rg.stats()
