@@ -482,7 +482,7 @@ def main():
     k_ms = float(np.mean(kernel_ms))
     achieved_gbs = L_STEP * BYTES_PER_SAMPLE / (k_ms * 1e-3) / 1e9
     achieved_tf = L_STEP * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12
-    kernel_name = f"stft_kernel<4096,ci16,acc> variant {variant}"
+    kernel_name = f"stft2_kernel<4096,ci16,acc> (K1v2) variant {variant}" if variant in (0, 20, 21, 22) else f"stft_kernel<4096,ci16,acc> variant {variant}"
     traffic, traffic_src = traffic_record(kernel_name)
     ring_gsps = world * L_STEP * e2e_steps / dt_ring
     e2e = {"value": round(ring_gsps / 1e6, 1), "unit": "Msamples/s",

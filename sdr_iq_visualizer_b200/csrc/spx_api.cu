@@ -553,6 +553,7 @@ int spx_plan_create(spx_plan** out, const spx_plan_config* cfg) {
             if ((rc = bluestein_plan_init(pl)) != SPX_OK) break;
         } else if (cfg->nfft > 8192) {
             if ((rc = bigfft_plan_init(pl)) != SPX_OK) break;
+            if ((rc = big2_plan_init(pl)) != SPX_OK) break;
         } else {
             std::vector<float2> tw = build_twiddles(cfg->nfft);
             if ((e = cudaMalloc(&pl->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) { rc = spx_set_error(SPX_E_NOMEM, "%s", cudaGetErrorString(e)); break; }
@@ -582,6 +583,8 @@ int spx_plan_destroy(spx_plan* pl) {
     if (pl->s_big_aux) { cudaStreamSynchronize(pl->s_big_aux); cudaStreamDestroy(pl->s_big_aux); }
     for (cudaEvent_t e : pl->ev_big) if (e) cudaEventDestroy(e);
     if (pl->d_big_tw) cudaFree(pl->d_big_tw);
+    if (pl->d_big2) cudaFree(pl->d_big2);
+    if (pl->d_big2_win) cudaFree(pl->d_big2_win);
     if (pl->d_blu) cudaFree(pl->d_blu);
     if (pl->blu_inner) spx_plan_destroy(pl->blu_inner);
     pl->st_big.release();

@@ -486,6 +486,8 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
                          unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
                          float vmax, cudaStream_t st, int sys_atomics) {
     const int n = pl->cfg.nfft;
+    if (big2_eligible(pl, in, db_rows, spec_rows))   // config-5 shape: one persistent kernel, scratch stays in L2
+        return big2_launch_stream(pl, in, frames, row0, wf_rows, welch_acc, maxhold, vmin, vmax, st, sys_atomics);
     const size_t frame_bytes = (size_t)n * sizeof(float2);
     // two halves of the scratch: the column kernel of batch k+1 (aux stream) runs next to the row kernel of batch k, so
     // the tail wave of one kernel is filled by the other instead of leaving SMs idle

@@ -143,6 +143,73 @@ SPX_HD void dft<16>(float2* v) {
 #undef SPX_SWAP
 }
 
+// ------------------------------------------------------------------ radix-16 DFT in fused-multiply-add form
+// Same 4 x 4 decomposition as dft<16>, but no W_16 twiddle is ever applied as a stand-alone multiply (Linzer-Feig
+// style): a factor c (1 - i t) is split into the two-FMA rotation (x + t y, y - t x) and the real scale c, and the
+// scale (cos(pi/8) or 1/sqrt 2) rides on the next butterfly as the multiplier of an FMA:  a +- c * b'.
+// 144 FP32 operations instead of 160 (64 + 16 + 22 + 20 + 22), the outer butterflies are packed FFMA2 on sm_100a.
+// Natural-order output, like dft<16>.
+SPX_HD float2 cfma(float2 b, float s, float2 a) {   // a + s * b
+#if defined(__CUDA_ARCH__) && SPX_PACKED_F32X2
+    return __ffma2_rn(b, make_float2(s, s), a);
+#else
+    return make_float2(fmaf(b.x, s, a.x), fmaf(b.y, s, a.y));
+#endif
+}
+#define SPX_T1 0.41421356237309504880f   // tan(pi/8)
+
+SPX_HD void dft16_fma(float2* v) {
+    dft4(v[0], v[4], v[8], v[12]);
+    dft4(v[1], v[5], v[9], v[13]);
+    dft4(v[2], v[6], v[10], v[14]);
+    dft4(v[3], v[7], v[11], v[15]);
+    // c' = 0: no twiddles
+    dft4(v[0], v[1], v[2], v[3]);
+    {   // c' = 1: y1 = v5 W^1 = C1 (x + t y, y - t x);  y2 = v6 W^2 = H (x + y, y - x);  y3 = v7 W^3 = C1 * (-i) (x - t y, y + t x)
+        const float2 p1 = make_float2(fmaf(SPX_T1, v[5].y, v[5].x), fmaf(-SPX_T1, v[5].x, v[5].y));
+        const float2 q3 = make_float2(fmaf(-SPX_T1, v[7].y, v[7].x), fmaf(SPX_T1, v[7].x, v[7].y));
+        const float2 p2 = make_float2(v[6].x + v[6].y, v[6].y - v[6].x);
+        const float2 t0 = cfma(p2, SPX_H, v[4]), t1 = cfma(p2, -SPX_H, v[4]);
+        // y3 / C1 = (q3.y, -q3.x);  t2' = p1 + y3/C1;  t3' = p1 - y3/C1;  u3' = -i t3' built directly in rotated form
+        const float2 t2 = make_float2(p1.x + q3.y, p1.y - q3.x);
+        const float2 u3 = make_float2(p1.y + q3.x, q3.y - p1.x);
+        v[4] = cfma(t2, SPX_C1, t0);
+        v[6] = cfma(t2, -SPX_C1, t0);
+        v[5] = cfma(u3, SPX_C1, t1);
+        v[7] = cfma(u3, -SPX_C1, t1);
+    }
+    {   // c' = 2: y1 = v9 W^2 = H (x + y, y - x);  y2 = v10 W^4 = (y, -x);  y3 = v11 W^6 = H (y - x, -(x + y))
+        const float2 p1 = make_float2(v[9].x + v[9].y, v[9].y - v[9].x);
+        const float2 p3 = make_float2(v[11].y - v[11].x, -(v[11].x + v[11].y));
+        const float2 t0 = make_float2(v[8].x + v[10].y, v[8].y - v[10].x);
+        const float2 t1 = make_float2(v[8].x - v[10].y, v[8].y + v[10].x);
+        const float2 t2 = cadd(p1, p3);
+        const float2 u3 = make_float2(p1.y - p3.y, p3.x - p1.x);      // -i (p1 - p3), built directly in rotated form
+        v[8] = cfma(t2, SPX_H, t0);
+        v[10] = cfma(t2, -SPX_H, t0);
+        v[9] = cfma(u3, SPX_H, t1);
+        v[11] = cfma(u3, -SPX_H, t1);
+    }
+    {   // c' = 3: y1 = v13 W^3 = C1 * (-i) (x - t y, y + t x);  y2 = v14 W^6 = H (y - x, -(x + y));  y3 = v15 W^9 = -C1 (x + t y, y - t x)
+        const float2 q1 = make_float2(fmaf(-SPX_T1, v[13].y, v[13].x), fmaf(SPX_T1, v[13].x, v[13].y));
+        const float2 q3 = make_float2(fmaf(SPX_T1, v[15].y, v[15].x), fmaf(-SPX_T1, v[15].x, v[15].y));
+        const float2 p2 = make_float2(v[14].y - v[14].x, -(v[14].x + v[14].y));
+        const float2 t0 = cfma(p2, SPX_H, v[12]), t1 = cfma(p2, -SPX_H, v[12]);
+        // y1 / C1 = (q1.y, -q1.x);  y3 / C1 = -q3
+        const float2 t2 = make_float2(q1.y - q3.x, -q1.x - q3.y);      // (y1 + y3) / C1
+        const float2 u3 = make_float2(q3.y - q1.x, -(q1.y + q3.x));    // -i (y1 - y3) / C1, directly in rotated form
+        v[12] = cfma(t2, SPX_C1, t0);
+        v[14] = cfma(t2, -SPX_C1, t0);
+        v[13] = cfma(u3, SPX_C1, t1);
+        v[15] = cfma(u3, -SPX_C1, t1);
+    }
+    // v[4c'+d] holds X[c'+4d]  ->  transpose the 4x4 register tile (pure renaming)
+    float2 t;
+#define SPX_SWAP(i, j) t = v[i]; v[i] = v[j]; v[j] = t;
+    SPX_SWAP(1, 4) SPX_SWAP(2, 8) SPX_SWAP(3, 12) SPX_SWAP(6, 9) SPX_SWAP(7, 13) SPX_SWAP(11, 14)
+#undef SPX_SWAP
+}
+
 // ------------------------------------------------------------------ compile-time plan
 // Radix of pass s for an N-point transform (0 when s >= number of passes).
 SPX_HD constexpr int plan_radix(int n, int s) {

@@ -37,6 +37,9 @@ struct spx_plan {
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_wn_fine = nullptr, *d_wn_coarse = nullptr;
     size_t big_scratch_bytes = 384u << 20;  // two halves of 192 MB: frames per batch = half / (nfft * 8); measured best on B200
     spx::DevBuf st_big;
+    float2* d_big2 = nullptr;      // K2v2 (single-kernel 65536-point path): N = 4096 twiddle table followed by the base table
+    size_t big2_tw_count = 0;
+    float* d_big2_win = nullptr;   // K2v2 window table in phase A's thread order
     cudaStream_t s_big_aux = nullptr;             // column kernels of batch k+1 run here, next to the row kernels of batch k
     cudaEvent_t ev_big[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // entry, A done x2, B done x2
     // Bluestein path (nfft not a power of two, or < 16): inner power-of-two plan of length blu_m
@@ -56,6 +59,10 @@ int bigfft_launch_stream(spx_plan* pl, const void* in, long long frames, long lo
                          unsigned char* wf_rows, float2* spec_rows, double* welch_acc, float* maxhold, float vmin,
                          float vmax, cudaStream_t st, int sys_atomics = 0);
 int peer_reduce_launch(const double* w_local, const float* m_local, double* w_peer, float* m_peer, long long n, cudaStream_t st);
+int big2_plan_init(spx_plan* pl);
+bool big2_eligible(const spx_plan* pl, const void* in, const float* db_rows, const float2* spec_rows);
+int big2_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, unsigned char* wf_rows, double* welch_acc,
+                       float* maxhold, float vmin, float vmax, cudaStream_t st, int sys_atomics);
 int welch_finalize_launch(const double* acc, int n, double inv_norm, double* pxx, double* pxx_db, cudaStream_t st);
 int bluestein_plan_init(spx_plan* pl);
 int bluestein_launch_stream(spx_plan* pl, const void* in, long long frames, long long row0, float* db_rows,

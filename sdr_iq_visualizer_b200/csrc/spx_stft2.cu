@@ -1,0 +1,46 @@
+// N = 1024 / 2048 / 4096 instantiations of K1v2 (warp-local first exchange, one block barrier per frame, swizzled TMA
+// tensor staging).  See spx_stft2_kernel.cuh / spx_stft2_device.cuh.
+#include "spx_stft2_kernel.cuh"
+
+namespace spx {
+
+tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)p;
+        else
+            cudaGetLastError();
+        tried = true;
+    }
+    return fn;
+}
+
+int launch_stft2(StftLaunch& L) {
+    if (L.variant == 22 || L.variant == 0) {   // default: FMA-form DFTs + uint8 index on the FMA / ALU pipes instead of F2I (XU)
+        switch (L.nfft) {
+            case 1024: return launch_stft2_n<1024, 2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L);
+            case 2048: return launch_stft2_n<2048, 2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L);
+            case 4096: return launch_stft2_n<4096, 2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L);
+        }
+    }
+    if (L.variant == 21) {   // radix-16 DFTs in fused-multiply-add form (dft16_fma)
+        switch (L.nfft) {
+            case 1024: return launch_stft2_n<1024, 2, TUNE_I2FP | TUNE_FMADFT>(L);
+            case 2048: return launch_stft2_n<2048, 2, TUNE_I2FP | TUNE_FMADFT>(L);
+            case 4096: return launch_stft2_n<4096, 2, TUNE_I2FP | TUNE_FMADFT>(L);
+        }
+    }
+    switch (L.nfft) {
+        case 1024: return launch_stft2_n<1024, 2, TUNE_I2FP>(L);
+        case 2048: return launch_stft2_n<2048, 2, TUNE_I2FP>(L);
+        case 4096: return launch_stft2_n<4096, 2, TUNE_I2FP>(L);
+        default: return spx_set_error(SPX_E_UNSUPPORTED, "K1v2 handles nfft 1024 / 2048 / 4096, not %d", L.nfft);
+    }
+}
+
+}  // namespace spx

@@ -1,10 +1,16 @@
 // N = 4096 instantiations of the fused STFT kernel (K1), including tuning variants.
-#include "spx_stft_kernel.cuh"
+#include "spx_stft2_kernel.cuh"
 
 namespace spx {
 int launch_stft_4k(StftLaunch& L) {
     switch (L.variant) {
-        case 0: return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);  // default: TMA-staged input, register twiddle bases, int16 -> float on the ALU pipe
+        case 0:    // default = K1v2 with FMA-form DFTs and the FMA-pipe colormap index (variant 22); K1 when frames are not 128-byte aligned
+        case 22:   // + colormap index without the XU pipe
+        case 21:   // K1v2 + FMA-form radix-16 DFTs
+        case 20:   // K1v2: warp-local first exchange, one barrier per frame
+            if (stft2_ok(L)) return launch_stft2(L);
+            return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);
+        case 12:   // round-1 default (K1: two block barriers per frame, bulk-copy staging, register twiddle bases) return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);  // default: TMA-staged input, register twiddle bases, int16 -> float on the ALU pipe
         case 8: return launch_stft_n<4096, TW_LDG, 2>(L);
         case 1: return launch_stft_n<4096, TW_LDG, 3>(L);
         case 2: return launch_stft_n<4096, TW_REG, 2>(L);

@@ -47,7 +47,9 @@ SPX_HD float2 ld_stream_cf32(const float2* p) {
     return *p;
 #endif
 }
-enum { TUNE_I2FP = 1 };  // kernel tuning bits (template parameter TUNE)
+// kernel tuning bits (template parameter TUNE).  FMADFT: radix-16 DFTs in FMA form (dft16_fma).  QFMA: the uint8 colormap
+// index is produced on the FMA / ALU pipes (saturating FMA, min, round-down FMA onto 2^23) instead of F2I on the XU pipe.
+enum { TUNE_I2FP = 1, TUNE_FMADFT = 2, TUNE_QFMA = 4 };
 
 // packed int16 I,Q -> float2.  Default: two I2F.S16 (XU pipe, 16 lanes/clk/SM).  TUNE_I2FP: sign-extend with
 // PRMT and convert with I2FP.F32.S32 (ALU pipe) -- exact either way (|v| <= 2^15 fits a float).
@@ -112,6 +114,23 @@ SPX_HD unsigned int sat_floor_u8(float q) {
     if (!(q == q)) return 0u;
     float f = floorf(q);
     return f < 0.f ? 0u : (f > 255.f ? 255u : (unsigned int)f);
+#endif
+}
+// The same index without the XU pipe: z = sat(y * q_a/256 + q_b/256) in [0, 1] (NaN -> 0, the scaling by 2^-8 is exact, so
+// 256 z is bit-for-bit the clamped quant_pre value), z = min(z, 1 - 2^-24), then fma.rm(z, 256, 2^23) = 2^23 + floor(256 z)
+// exactly: the index is the low byte of the result's bit pattern, which a byte store writes as is.
+SPX_HD unsigned int sat_floor_u8_fma(float y, float q_a256, float q_b256) {
+#ifdef __CUDA_ARCH__
+    float z, r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(z) : "f"(y), "f"(q_a256), "f"(q_b256));
+    z = fminf(z, 0.99999994f);
+    asm("fma.rm.f32 %0, %1, 0f43800000, 0f4B000000;" : "=f"(r) : "f"(z));
+    return __float_as_uint(r);       // callers store the low byte
+#else
+    float z = fmaf(y, q_a256, q_b256);
+    if (!(z == z) || z < 0.f) z = 0.f;
+    if (z > 0.99999994f) z = 0.99999994f;
+    return (unsigned int)floorf(z * 256.0f);
 #endif
 }
 #define SPX_DB_PER_LOG2 6.02059991327962390427f  // 20*log10(2)
@@ -305,7 +324,7 @@ SPX_HD constexpr int shift_off(int t) {
     return (t * (N / R) + N / 2) & (N - 1);
 }
 
-template <int N, bool ACC>
+template <int N, bool ACC, int TUNE = 0>
 SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, StftAcc<ACC>& acc) {
     constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S), NB = 16 / R, T = N / 16;
     if (p.spec_rows) {
@@ -347,11 +366,20 @@ SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, Stf
         }
         if (p.wf_rows) {
             unsigned char* wf = p.wf_rows + row * N + tid;
+            if constexpr ((TUNE & TUNE_QFMA) != 0) {
+                const float qa = p.q_a * 0.00390625f, qb = p.q_b * 0.00390625f;
 #pragma unroll
-            for (int u = 0; u < NB; ++u)
+                for (int u = 0; u < NB; ++u)
 #pragma unroll
-                for (int t = 0; t < R; ++t)
-                    wf[shift_off<N>(t) + T * u] = (unsigned char)sat_floor_u8(quant_pre(v[u * R + t].y, p.q_a, p.q_b));
+                    for (int t = 0; t < R; ++t)
+                        wf[shift_off<N>(t) + T * u] = (unsigned char)sat_floor_u8_fma(v[u * R + t].y, qa, qb);
+            } else {
+#pragma unroll
+                for (int u = 0; u < NB; ++u)
+#pragma unroll
+                    for (int t = 0; t < R; ++t)
+                        wf[shift_off<N>(t) + T * u] = (unsigned char)sat_floor_u8(quant_pre(v[u * R + t].y, p.q_a, p.q_b));
+            }
         }
     }
 }

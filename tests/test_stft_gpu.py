@@ -74,7 +74,7 @@ def test_4096_pipelined_rows_only_kernel(sp, fmt, hop, L):
     x = sref.synth_iq(L, seed=41)
     x = sref.to_ci16(x) if fmt else x.astype(np.complex64)
     pl = sp.SpectralPlan(n, hop, "hann", fmt, variant=11)
-    ref = sp.SpectralPlan(n, hop, "hann", fmt, variant=0)
+    ref = sp.SpectralPlan(n, hop, "hann", fmt, variant=12)     # K1 (round-1 default): same per-thread arithmetic
     vmin, vmax = (0.0, 130.0) if fmt else (-60.0, 60.0)
     r = pl.stft(x, db_rows=True, wf_rows=True, spectrum=True, vmin=vmin, vmax=vmax)
     r0 = ref.stft(x, db_rows=True, wf_rows=True, spectrum=True, vmin=vmin, vmax=vmax)
@@ -87,7 +87,7 @@ def test_4096_pipelined_rows_only_kernel(sp, fmt, hop, L):
     pl.close(); ref.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 def test_4096_kernel_variants_agree(sp, variant):
     n, hop = 4096, 1024
     x = sref.to_ci16(sref.synth_iq(n + 300 * hop, seed=77))
@@ -99,6 +99,69 @@ def test_4096_kernel_variants_agree(sp, variant):
     parity.check_power(r.welch_acc[0], P.sum(axis=0), what="welch")
     parity.check_power(r.maxhold[0], P.max(axis=0), what="maxhold")
     parity.check_u8(r.wf_rows, sref.amplitude_db(X), 0.0, 130.0)
+    pl.close()
+
+
+@pytest.mark.parametrize("variant", [20, 21, 22])
+@pytest.mark.parametrize("nfft,hop,kind,fmt", [(4096, 1024, "hann", 1), (4096, 4096, "rect", 0), (4096, 2048, "blackman", 0),
+                                               (2048, 1024, "hann", 0), (2048, 512, "hann", 1), (1024, 512, "hann", 0),
+                                               (1024, 256, "blackman", 1)])
+def test_k1v2_warp_local_exchange_kernel(sp, variant, nfft, hop, kind, fmt):
+    """K1v2 (spx_stft2_kernel.cuh: swizzled TMA tensor staging, warp-local first exchange, one barrier per frame; variant
+    21 adds the FMA-form radix-16 DFT): oracle parity on many frames per CTA with a ragged tail; for N = 4096 variant 20
+    is bit-identical to K1 (same arithmetic, different data flow)."""
+    L = nfft + hop * 2999 + min(5, hop - 1)
+    xc = sref.synth_iq(L, seed=nfft + hop + variant)
+    x = sref.to_ci16(xc) if fmt else xc.astype(np.complex64)
+    vmin, vmax = (0.0, 130.0) if fmt else (-60.0, 60.0)
+    pl = sp.SpectralPlan(nfft, hop, kind, fmt, variant=variant)
+    r = pl.stft(x, db_rows=True, wf_rows=True, spectrum=True, welch=True, maxhold=True, vmin=vmin, vmax=vmax)
+    assert r.n_frames == 3000
+    nchk = 64
+    X = oracle_rows(x[: 2 * (nfft + (nchk - 1) * hop)] if fmt else x[: nfft + (nchk - 1) * hop], nfft, hop, kind, fmt=fmt)
+    P = X.real**2 + X.imag**2
+    assert np.abs(r.spectrum[:nchk] - X).max() <= 5e-6 * np.sqrt(P.mean())
+    parity.check_db_rows(r.db_rows[:nchk], P, what=f"K1v2 v{variant} N={nfft}")
+    parity.check_u8(r.wf_rows[:nchk], sref.amplitude_db(X), vmin, vmax, what=f"K1v2 v{variant} u8")
+    ref = sp.SpectralPlan(nfft, hop, kind, fmt, variant=12)    # K1, the round-1 kernel
+    r0 = ref.stft(x, db_rows=True, wf_rows=True, spectrum=True, welch=True, maxhold=True, vmin=vmin, vmax=vmax)
+    if variant == 20 and nfft == 4096:
+        np.testing.assert_array_equal(r.spectrum, r0.spectrum)
+        np.testing.assert_array_equal(r.wf_rows, r0.wf_rows)
+        np.testing.assert_array_equal(r.maxhold, r0.maxhold)
+    else:   # every frame against K1 (itself oracle-checked above and elsewhere): tail frames, chunk flushes
+        assert np.abs(r.spectrum - r0.spectrum).max() <= 4e-6 * np.sqrt(P.mean())
+        assert np.abs(r.wf_rows.astype(np.int16) - r0.wf_rows.astype(np.int16)).max() <= 1
+    parity.check_power(r.welch_acc[0], r0.welch_acc[0], what=f"K1v2 v{variant} welch vs K1", rel_tol=2e-5)
+    parity.check_power(r.maxhold[0], r0.maxhold[0], what=f"K1v2 v{variant} maxhold vs K1", rel_tol=2e-5)
+    if variant == 22:   # the FMA-pipe colormap index is bit-for-bit the F2I one
+        alt = sp.SpectralPlan(nfft, hop, kind, fmt, variant=21)
+        r1 = alt.stft(x, wf_rows=True, vmin=vmin, vmax=vmax)
+        np.testing.assert_array_equal(r.wf_rows, r1.wf_rows)
+        alt.close()
+    pl.close(); ref.close()
+
+
+def test_k1v2_multistream_and_unaligned_fallback(sp):
+    """n_streams > 1 through the tensor map (stream stride a multiple of 128 bytes) and the fallback to K1 when the hop is
+    not 128-byte aligned."""
+    n, hop, S = 2048, 1024, 5
+    L = n + 40 * hop
+    xs = np.concatenate([sref.synth_iq(L, seed=30 + s, snr_db=4 * (s + 1)) for s in range(S)]).astype(np.complex64)
+    pl = sp.SpectralPlan(n, hop, "hann", variant=20)
+    r = pl.stft(xs, n_streams=S, welch=True, maxhold=True, db_rows=True)
+    X = oracle_rows(xs, n, hop, "hann", n_streams=S)
+    P = (X.real**2 + X.imag**2).reshape(S, -1, n)
+    parity.check_db_rows(r.db_rows, P.reshape(-1, n), what="K1v2 streams")
+    for s in range(S):
+        parity.check_power(r.welch_acc[s], P[s].sum(axis=0), what=f"K1v2 welch s={s}")
+        parity.check_power(r.maxhold[s], P[s].max(axis=0), what=f"K1v2 maxhold s={s}")
+    pl.close()
+    pl = sp.SpectralPlan(4096, 1023, "hann", variant=20)      # odd hop: frames are not 128-byte aligned -> K1 direct loads
+    x = sref.synth_iq(4096 + 1023 * 20, seed=3).astype(np.complex64)
+    r = pl.stft(x, db_rows=True)
+    X = oracle_rows(x, 4096, 1023, "hann")
+    parity.check_db_rows(r.db_rows, X.real**2 + X.imag**2, what="K1v2 fallback")
     pl.close()
 
 
@@ -301,6 +364,39 @@ def test_config5_prefix(sp):
     parity.check_power(r.maxhold[0], P.max(axis=0), what="C5 maxhold")
     parity.check_u8(r.wf_rows, sref.amplitude_db(X), -20.0, 110.0, what="C5 u8")
     pl.close()
+
+
+@pytest.mark.parametrize("hop,frames,kind,outs", [(32768, 1, "hann", "all"), (32768, 2, "hann", "all"), (32768, 19, "blackman", "all"),
+                                                   (32768, 127, "hann", "all"), (65536, 40, "rect", "rows"), (16384, 90, "hann", "acc"),
+                                                   (256, 37, "hann", "all")])
+def test_k2v2_single_kernel_65536(sp, hop, frames, kind, outs):
+    """K2v2 (spx_big2.cu: one persistent kernel, role A / role B per CTA, scratch resident in L2, counters between the
+    16 CTAs of a lane): oracle parity and agreement with the two-kernel path (variant 1).  Frame counts below, at and above
+    the lane count (single-frame lanes, uneven lanes, scratch slots wrapping around), hops down to 256 samples."""
+    n = 65536
+    L = n + hop * (frames - 1) + 77
+    x = sref.synth_iq(L, seed=frames + hop, tone_cycles_per_sample=20000.37 / 65536).astype(np.complex64)
+    vmin, vmax = -20.0, 110.0
+    kw = dict(wf_rows=outs in ("all", "rows"), welch=outs in ("all", "acc"), maxhold=outs in ("all", "acc"), vmin=vmin, vmax=vmax)
+    pl = sp.SpectralPlan(n, hop, kind)
+    old = sp.SpectralPlan(n, hop, kind, variant=1)
+    r, r0 = pl.stft(x, **kw), old.stft(x, **kw)
+    assert r.n_frames == r0.n_frames == frames
+    nchk = min(frames, 6)
+    sel = sorted(set(range(nchk)) | set(range(max(0, frames - 3), frames)))
+    X = np.stack([oracle_rows(x[f * hop: f * hop + n], n, n, kind)[0] for f in sel])
+    if kw["wf_rows"]:
+        parity.check_u8(r.wf_rows[sel], sref.amplitude_db(X), vmin, vmax, what=f"K2v2 u8 F={frames}")
+        assert np.abs(r.wf_rows.astype(np.int16) - r0.wf_rows.astype(np.int16)).max() <= 1      # every row vs the two-kernel path
+        assert (r.wf_rows != r0.wf_rows).mean() < 2e-3
+    if kw["welch"]:
+        parity.check_power(r.welch_acc[0], r0.welch_acc[0], what="K2v2 welch vs two-kernel path", rel_tol=1.5e-4)
+        parity.check_power(r.maxhold[0], r0.maxhold[0], what="K2v2 maxhold vs two-kernel path", rel_tol=1.5e-4)
+        if frames <= 6:
+            P = X.real**2 + X.imag**2
+            parity.check_power(r.welch_acc[0], P.sum(axis=0), what="K2v2 welch")
+            parity.check_power(r.maxhold[0], P.max(axis=0), what="K2v2 maxhold")
+    pl.close(); old.close()
 
 
 @pytest.mark.parametrize("nfft,hop,fmt,L", [(4096, 1024, 1, 300_000), (65536, 32768, 0, 1 << 21)])
