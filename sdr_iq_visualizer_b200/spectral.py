@@ -265,12 +265,14 @@ _plans: dict = {}
 _plans_lock = threading.Lock()
 
 
-def get_plan(nfft, hop=None, window="rect", in_fmt=FMT_CF32, in_scale=1.0, db_eps=DB_EPS_REFERENCE, device=0) -> SpectralPlan:
-    key = (int(nfft), int(hop or nfft), window_id(window), int(in_fmt), float(in_scale), float(db_eps), int(device))
+def get_plan(nfft, hop=None, window="rect", in_fmt=FMT_CF32, in_scale=1.0, db_eps=DB_EPS_REFERENCE, device=0,
+             variant=0) -> SpectralPlan:
+    key = (int(nfft), int(hop or nfft), window_id(window), int(in_fmt), float(in_scale), float(db_eps), int(device), int(variant))
     with _plans_lock:
         pl = _plans.get(key)
         if pl is None:
-            pl = SpectralPlan(*key[:2], window=key[2], in_fmt=key[3], in_scale=key[4], db_eps=key[5], device=key[6])
+            pl = SpectralPlan(*key[:2], window=key[2], in_fmt=key[3], in_scale=key[4], db_eps=key[5], device=key[6],
+                              variant=key[7])
             _plans[key] = pl
         return pl
 
