@@ -144,6 +144,16 @@ SPX_API int spx_allreduce_welch(spx_comm* comm, double* welch_acc, float* maxhol
 SPX_API int spx_gather_rows(spx_comm* comm, const void* rows_local, int64_t local_bytes, void* rows_all,
                             const int64_t* bytes_per_rank, int dst, void* stream);
 
+/* The reference's per-buffer stream path in float64 (/root/reference/app/sdr/streamer.py:119-121): fftshift(fft(x)) and
+ * 20*log10(|X| + eps), one rx buffer per call, power-of-two n in [2, 8192].  samples: complex128 (in_is_c128 = 1, what
+ * pyadi-iio's rx() returns, :114) or complex64; power_db_out float64[n] / spec_out complex128[n] (both in fftshift
+ * order) / wf_row uint8[n] (colormap index of the dB values, needs vmax > vmin): any subset.  With SPX_MEM_HOST the
+ * call copies in and out and waits; with SPX_MEM_DEVICE it only enqueues on `stream`.  Agrees with numpy to ~1e-12 dB;
+ * the batched STFT path (spx_stft_exec) computes in float32. */
+SPX_API int spx_stream_frame_f64(int device, int mem, const void* samples, int in_is_c128, int n, double eps,
+                                 double* power_db_out, double* spec_out, uint8_t* wf_row, double vmin, double vmax,
+                                 void* stream);
+
 /* ---------------------------------------------------------------- STFT plan */
 typedef struct spx_plan spx_plan;
 

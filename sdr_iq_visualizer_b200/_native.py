@@ -150,6 +150,8 @@ _SIGNATURES = {
     "spx_nccl_destroy": (C.c_int, [C.c_void_p]),
     "spx_allreduce_welch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "spx_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "spx_stream_frame_f64": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     "spx_timer_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "spx_timer_start": (C.c_int, [C.c_void_p, C.c_void_p]),
     "spx_timer_stop": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -118,7 +118,7 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
             tma_load_tile(stage_u32, &tm_in, 32 * g, p.in_row0 + (lane + s * p.lanes) * p.hop_rows, full_u32);
         } else {
             const int slot = s % slots;
-            const int target = 128 * (s / slots + 1);      // 16 CTAs x 8 warps release once per visit of the slot
+            const int target = 16 * (s / slots + 1);       // the 16 CTAs of the lane release once per visit of the slot
             // the tile is read by the TMA unit straight from L2 (the point of coherence), never through this SM's L1: a
             // relaxed poll is enough, no L1 invalidation (an acquire load flushes L1 and the local-memory lines in it)
             while (ld_relaxed_gpu(done + slot) < target) __nanosleep(100);
@@ -126,43 +126,44 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
             tma_load_tile(stage_u32, &tm_t, 32 * g, (lane * slots + slot) * 256, full_u32);
         }
     };
-    auto release = [&](int slot) {   // this warp's scratch stores of an A role are visible device-wide before the increment
-        __syncwarp();
-        if ((tid & 31) == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(done + slot) : "memory");
+    // Release of an A role (its scratch stores become visible device-wide before the counter moves): ONE fence per CTA and
+    // role, issued by one lane after a block barrier that orders every warp's stores before it (cumulativity).  The fence
+    // (MEMBAR.GPU, ~0.5 us even with no store in flight) is paid by a different warp each role.
+    auto release = [&](int slot, int duty_warp) {
+        if (tid == 32 * duty_warp) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(done + slot) : "memory");
     };
-    auto store_run = [&](int buf, long long f) {   // run k2s = tid of row f: 16 consecutive bins 256 k2s + 16 g .. + 15
+    auto store_run = [&](int buf, int s_row) {   // run k2s = tid of the row of frame s_row: 16 consecutive bins 256 k2s + 16 g .. + 15
         const uint4 run = *reinterpret_cast<const uint4*>(u8tile + buf * 4096 + 16 * tid);
+        const long long f = lane + (long long)s_row * p.lanes;
         __stcs(reinterpret_cast<uint4*>(p.wf_rows + (size_t)(p.row0 + f) * BIG2_N + 256 * tid + 16 * g), run);
     };
 
     Big2Seq cur{0, 0};
-    unsigned parity = 0;
-    int u8buf = 0, frames_in_acc = 0;
-    int pend_slot = -1;            // A role whose release is still owed (done one role later, when its stores have landed)
-    long long pend_row = -1;       // B role whose uint8 tile is still to be stored (after the next block barrier)
+    unsigned parity = 0;           // bit 0: phase parity of the staging barrier; the role counter lives in bits 1..
+    int pend_slot = -1;            // A role whose release is still owed (done one role later, behind the next block barrier)
+    int pend_s = -1;               // B role (frame index s) whose uint8 tile is still to be stored (same place)
     float2 v[16];
     if (tid == 0) issue(0, 0);
     while (true) {
         const int kind = cur.ph, s = cur.s(lag);
         Big2Seq nx = cur;
         const bool has_next = nx.advance(n_l, lag);
-        const int nkind = nx.ph, ns = nx.s(lag);
         // the next role is the B role of the very frame this A role produces (a lane with a single frame): its tile can only
         // be requested after this role's release
-        const bool hold = has_next && kind == 0 && nkind == 1 && ns == s;
-        mbar_wait(full_u32, parity);
-        parity ^= 1u;
+        const bool hold = has_next && kind == 0 && nx.ph == 1 && nx.s(lag) == s;
+        mbar_wait(full_u32, parity & 1u);
+        parity += 1u;
         big2_phase_a<BIG2_TUNE>(v, tid, stage, kind == 0 ? wf_ptr : nullptr, X);
-        __syncthreads();       // the staged tile is consumed; the previous role's uint8 tile is complete
-        if (pend_slot >= 0) {  // release of the previous A role: its stores were issued most of a role ago, the fence is cheap now
-            release(pend_slot);
+        __syncthreads();       // the staged tile is consumed; the previous role's stores are issued, its uint8 tile complete
+        if (pend_slot >= 0) {
+            release(pend_slot, (parity >> 1) & 7);
             pend_slot = -1;
         }
-        if (pend_row >= 0) {
-            store_run(u8buf ^ 1, pend_row);
-            pend_row = -1;
+        if (pend_s >= 0) {
+            store_run(pend_s & 1, pend_s);
+            pend_s = -1;
         }
-        if (tid == 0 && has_next && !hold) issue(nkind, ns);   // refill the staging tile: overlaps the rest of this role
+        if (tid == 0 && has_next && !hold) issue(nx.ph, nx.s(lag));   // refill the staging tile: overlaps the rest of this role
         k2_phase_b1<4096, BIG2_TUNE>(v, tid, X, twr);
         if (kind == 0) {
             const int slot = s % slots;
@@ -170,35 +171,29 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
             big2_twiddle_store<BIG2_TUNE>(v, tid, bases, t_tile);
             pend_slot = slot;
             if (hold) {
-                release(slot);
-                pend_slot = -1;
                 __syncthreads();
-                if (tid == 0) issue(nkind, ns);
+                release(slot, 0);
+                pend_slot = -1;
+                if (tid == 0) issue(nx.ph, nx.s(lag));
             }
         } else {
-            big2_epilogue<ACC, BIG2_TUNE>(v, tid, p.db_eps, p.db_pw_min, p.q_a, p.q_b, p.wf_rows != nullptr, acc, u8tile + u8buf * 4096);
-            if (p.wf_rows != nullptr) {
-                pend_row = lane + (long long)s * p.lanes;
-                u8buf ^= 1;
-            }
+            big2_epilogue<ACC, BIG2_TUNE>(v, tid, p.db_eps, p.db_pw_min, p.q_a, p.q_b, p.wf_rows != nullptr, acc, u8tile + (s & 1) * 4096);
+            if (p.wf_rows != nullptr) pend_s = s;
             if (ACC) {
-                ++frames_in_acc;
-                if (frames_in_acc == 256 || s + 1 == n_l) {   // bound the float32 accumulation like K1's chunks
+                if ((s & 255) == 255 || s + 1 == n_l) {   // bound the float32 accumulation like K1's chunks
 #pragma unroll
                     for (int kb = 0; kb < 16; ++kb)
                         flush_acc(p.welch_acc, p.maxhold, big2_acc_pos(g, tid, kb), acc.sum[kb], acc.mx[kb], p.sys_atomics);
                     acc.reset();
-                    frames_in_acc = 0;
                 }
             }
         }
         if (!has_next) break;
         cur = nx;
     }
-    if (pend_slot >= 0) release(pend_slot);     // (cannot happen: the last role of a lane is a B role)
-    if (pend_row >= 0) {
+    if (pend_s >= 0) {
         __syncthreads();
-        store_run(u8buf ^ 1, pend_row);
+        store_run(pend_s & 1, pend_s);
     }
 }
 

@@ -10,7 +10,8 @@ int launch_stft_4k(StftLaunch& L) {
         case 20:   // K1v2: warp-local first exchange, one barrier per frame
             if (stft2_ok(L)) return launch_stft2(L);
             return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);
-        case 12:   // round-1 default (K1: two block barriers per frame, bulk-copy staging, register twiddle bases) return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);  // default: TMA-staged input, register twiddle bases, int16 -> float on the ALU pipe
+        case 12:   // round-1 default (K1: two block barriers per frame, bulk-copy staging, register twiddle bases)
+            return launch_stft_n<4096, TW_REG, 2, true, TUNE_I2FP>(L);  // default: TMA-staged input, register twiddle bases, int16 -> float on the ALU pipe
         case 8: return launch_stft_n<4096, TW_LDG, 2>(L);
         case 1: return launch_stft_n<4096, TW_LDG, 3>(L);
         case 2: return launch_stft_n<4096, TW_REG, 2>(L);

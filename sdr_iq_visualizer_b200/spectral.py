@@ -289,9 +289,28 @@ def stream_frame(samples, sample_rate: float, center_freq: float, eps: float = D
     """Drop-in for the three hot lines of the reference stream loop (streamer.py:119-121):
     returns ``(freqs, power_db)``, both float64[N] in fftshift order, for one rx buffer of any length.
     With ``wf_range=(vmin, vmax)`` the same launch also emits the uint8 waterfall row of the frame and the
-    return value is ``(freqs, power_db, wf_row)``."""
+    return value is ``(freqs, power_db, wf_row)``.
+
+    Power-of-two buffers up to 8192 samples (the reference's default is 4096, streamer.py:10) run the float64 kernel
+    (``spx_stream_frame_f64``): the reference computes this path in float64 and, at ~244 buffers/s, precision is what
+    matters.  Other lengths go through the float32 plan (Bluestein / four-step kernels)."""
     x = np.asarray(samples)
     n = x.shape[0]
+    if 2 <= n <= 8192 and (n & (n - 1)) == 0:
+        nat.require_device()
+        if x.dtype != np.complex64:
+            x = np.ascontiguousarray(x, dtype=np.complex128)   # pyadi-iio rx() already returns complex128 (streamer.py:114)
+        else:
+            x = np.ascontiguousarray(x)
+        pdb = np.empty(n, np.float64)
+        wf = np.empty(n, np.uint8) if wf_range is not None else None
+        vmin, vmax = (float(wf_range[0]), float(wf_range[1])) if wf_range is not None else (0.0, 1.0)
+        nat.check(nat.lib().spx_stream_frame_f64(int(device), MEM_HOST, x.ctypes.data, 1 if x.dtype == np.complex128 else 0, n,
+                                                  float(eps), pdb.ctypes.data, None, None if wf is None else wf.ctypes.data,
+                                                  vmin, vmax, None))
+        if wf is None:
+            return freq_axis(n, sample_rate, center_freq), pdb
+        return freq_axis(n, sample_rate, center_freq), pdb, wf
     pl = get_plan(n, n, "rect", FMT_CF32, 1.0, eps, device)
     if wf_range is None:
         res = pl.stft(x, db_rows=True)

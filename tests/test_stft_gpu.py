@@ -29,20 +29,44 @@ def oracle_rows(x, nfft, hop, kind, fmt=0, scale=1.0, n_streams=1):
 
 
 def test_stream_frames_match_reference_golden(sp, golden_stream):
-    """spectral.stream_frame == reference _stream_data outputs (streamer.py:119-121)."""
+    """spectral.stream_frame == reference _stream_data outputs (streamer.py:119-121).  The drop-in runs the float64 kernel
+    for these buffer sizes: every bin, above or below the noise floor, within 1e-9 dB of what the reference produced
+    (the north_star bar is 1e-3 dB above the floor, 1e-4 relative below it)."""
     z, meta = golden_stream
+    worst = 0.0
     for m in meta:
         k = m["key"]
         f, p = sp.stream_frame(z[k + "_samples"], m["sample_rate"], m["center_freq"])
         assert f.dtype == np.float64 and p.dtype == np.float64 and p.shape == (m["n"],)
         np.testing.assert_array_equal(f, z[k + "_freqs"])           # integer permutation + exact axis
         ref = z[k + "_power_db"]
-        P = (10 ** (ref / 20) - 1e-12).clip(min=0) ** 2
         if np.all(ref == -240.0):
-            assert np.abs(p + 240.0).max() < 1e-3
-        else:
-            parity.check_db_rows(p[None, :], P[None, :], what=k)
-            assert int(np.argmax(p)) == int(np.argmax(ref))
+            np.testing.assert_array_equal(p, ref)
+            continue
+        # bins whose magnitude is comparable with eps = 1e-12 are excluded from the dB comparison only where the reference
+        # itself is at its -240 dB clamp; everywhere else the comparison is on every bin
+        err = np.abs(p - ref)
+        worst = max(worst, float(err.max()))
+        assert err.max() <= 1e-9, (k, float(err.max()))
+        P = (10 ** (ref / 20) - 1e-12).clip(min=0) ** 2
+        parity.check_db_rows(p[None, :], P[None, :], what=k + " (float64 stream kernel)")
+        assert int(np.argmax(p)) == int(np.argmax(ref))
+    parity._record("stream_f64", "golden stream frames", worst_abs_db_any_bin=worst)
+
+
+def test_stream_frame_float32_plan_path_on_goldens(sp, golden_stream):
+    """The same golden frames through the float32 STFT plan (the path a buffer size outside [2, 8192] or not a power of two
+    takes, and the arithmetic of the batched kernels): the north_star tolerance, with the observed margin recorded."""
+    z, meta = golden_stream
+    for m in meta:
+        k = m["key"]
+        ref = z[k + "_power_db"]
+        if np.all(ref == -240.0) or m["n"] < 16:
+            continue
+        pl = sp.get_plan(m["n"], m["n"], "rect", sp.FMT_CF32, 1.0, 1e-12, 0, variant=12)
+        p = pl.stft(z[k + "_samples"], db_rows=True).db_rows[0].astype(np.float64)
+        P = (10 ** (ref / 20) - 1e-12).clip(min=0) ** 2
+        parity.check_db_rows(p[None, :], P[None, :], what=k + " (float32 plan, K1)")
 
 
 @pytest.mark.parametrize("nfft,hop,kind", [(16, 16, "rect"), (32, 8, "hann"), (64, 16, "blackman"), (128, 128, "hann"),
