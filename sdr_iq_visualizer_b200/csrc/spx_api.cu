@@ -583,6 +583,7 @@ int spx_plan_destroy(spx_plan* pl) {
     if (pl->s_big_aux) { cudaStreamSynchronize(pl->s_big_aux); cudaStreamDestroy(pl->s_big_aux); }
     for (cudaEvent_t e : pl->ev_big) if (e) cudaEventDestroy(e);
     if (pl->d_big_tw) cudaFree(pl->d_big_tw);
+    if (pl->ev_scratch) cudaEventDestroy(pl->ev_scratch);
     if (pl->d_big2) cudaFree(pl->d_big2);
     if (pl->d_big2_win) cudaFree(pl->d_big2_win);
     if (pl->d_blu) cudaFree(pl->d_blu);
@@ -717,14 +718,27 @@ int spx_stft_exec(spx_plan* pl, spx_stft_args* a) {
     if (a->in == nullptr && F > 0) return spx_set_error(SPX_E_INVALID, "in is NULL");
     if (a->mem == SPX_MEM_DEVICE) {
         cudaStream_t st = a->stream ? (cudaStream_t)a->stream : pl->s_compute;
+        // Plan-owned scratch (four-step / K2v2 scratch and counters, Bluestein buffers, peer staging) is shared by every
+        // call on this plan: a call on another stream than the previous one waits for that one's kernels first.
+        const bool owns_scratch = pl->cfg.nfft > 8192 || pl->blu_m != 0 || a->peer_outputs;
+        if (owns_scratch) {
+            if (!pl->ev_scratch) SPX_CUDA(cudaEventCreateWithFlags(&pl->ev_scratch, cudaEventDisableTiming));
+            if (pl->scratch_stream_valid && pl->scratch_stream != st) SPX_CUDA(cudaStreamWaitEvent(st, pl->ev_scratch, 0));
+        }
         if (!a->accumulate) {
             if (a->welch_acc) SPX_CUDA(cudaMemsetAsync(a->welch_acc, 0, (size_t)S * N * sizeof(double), st));
             if (a->maxhold) SPX_CUDA(cudaMemsetAsync(a->maxhold, 0, (size_t)S * N * sizeof(float), st));
         }
-        if (a->peer_outputs && !a->db_rows && !a->spec_rows && F > 0) return stft_exec_device_peer(pl, a, F, st);
-        return stft_launch_device(pl, a->in, S, a->stream_stride, F, a->db_rows, a->wf_rows,
-                                  reinterpret_cast<float2*>(a->spec_rows), a->welch_acc, a->maxhold, a->vmin, a->vmax, st,
-                                  a->peer_outputs ? 1 : 0);
+        int rc;
+        if (a->peer_outputs && !a->db_rows && !a->spec_rows && F > 0) rc = stft_exec_device_peer(pl, a, F, st);
+        else rc = stft_launch_device(pl, a->in, S, a->stream_stride, F, a->db_rows, a->wf_rows, reinterpret_cast<float2*>(a->spec_rows),
+                                     a->welch_acc, a->maxhold, a->vmin, a->vmax, st, a->peer_outputs ? 1 : 0);
+        if (rc == SPX_OK && owns_scratch) {
+            SPX_CUDA(cudaEventRecord(pl->ev_scratch, st));
+            pl->scratch_stream = st;
+            pl->scratch_stream_valid = true;
+        }
+        return rc;
     }
     if (F == 0) {
         if (!a->accumulate) {

@@ -46,6 +46,10 @@ struct spx_plan {
     int blu_m = 0;
     spx_plan* blu_inner = nullptr;
     float2* d_blu = nullptr;  // [N] window*scale*chirp, [N] chirp/M, [M] FFT_M(conj chirp) in fftshift order
+    // ordering of plan-owned scratch between calls on different streams
+    cudaEvent_t ev_scratch = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_stream_valid = false;
     std::mutex mu;
 };
 

@@ -199,27 +199,6 @@ def run_c5(ctx, collective="fused", rows="gather", log2_samples=30, steps=5, war
         if tr is not local_rows:
             tr.free()
 
-    if gather and collective == "fused":
-        # NVLink ingress floor of the gather: the rows of ranks 1..G-1 pushed by the copy engines alone, all at once
-        remote = (F - (sd.frame_block(F, 0, world)[1])) * N
-        out["gather_remote_bytes"] = int(remote)
-        if world > 1:
-            src = nat.DeviceArray((max(F_local, 1) * N,), np.uint8, dev)
-            best = 1e30
-            for _ in range(3):
-                ctx.barrier()
-                t1 = time.perf_counter()
-                if rank != 0 and F_local > 0:
-                    nat.check(ctx.lib.spx_memcpy_d2d_async(dev, rows_view.rows(sh.f0, sh.f1).ptr, src.ptr, F_local * N, pl.stream))
-                pl.sync()
-                ctx.barrier()
-                best = min(best, ctx.reduce_max(time.perf_counter() - t1))
-            src.free()
-            out["nvlink_ingress_gbs_measured"] = round(remote / best / 1e9, 1)
-            out["gather_floor_ms"] = round(best * 1e3, 3)
-            out["gather_vs_floor"] = round(out["ms_per_step"] / (best * 1e3), 3)
-            out["nvlink_gbs_achieved"] = round(remote / (out["ms_per_step"] * 1e-3) / 1e9, 1)
-
     if check:
         from tests import parity
         chk = PeriodicChecker(block, N, hop)
@@ -256,6 +235,28 @@ def run_c5(ctx, collective="fused", rows="gather", log2_samples=30, steps=5, war
             if ok > 0.5 else "FAILED"
         if ok < 0.5:
             raise SystemExit("c5 parity check failed")
+
+    if gather and collective == "fused":
+        # NVLink ingress floor of the gather: the row bytes of ranks 1..G-1 pushed by the copy engines alone, all at once
+        # (after the parity check: the probe overwrites the gathered rows with scratch data)
+        remote = (F - (sd.frame_block(F, 0, world)[1])) * N
+        out["gather_remote_bytes"] = int(remote)
+        if world > 1:
+            src = nat.DeviceArray((max(F_local, 1) * N,), np.uint8, dev)
+            best = 1e30
+            for _ in range(3):
+                ctx.barrier()
+                t1 = time.perf_counter()
+                if rank != 0 and F_local > 0:
+                    nat.check(ctx.lib.spx_memcpy_d2d_async(dev, rows_view.rows(sh.f0, sh.f1).ptr, src.ptr, F_local * N, pl.stream))
+                pl.sync()
+                ctx.barrier()
+                best = min(best, ctx.reduce_max(time.perf_counter() - t1))
+            src.free()
+            out["nvlink_ingress_gbs_measured"] = round(remote / best / 1e9, 1)
+            out["gather_floor_ms"] = round(best * 1e3, 3)
+            out["gather_vs_floor"] = round(out["ms_per_step"] / (best * 1e3), 3)
+            out["nvlink_gbs_achieved"] = round(remote / (out["ms_per_step"] * 1e-3) / 1e9, 1)
 
     if collective == "fused":
         for t in targets:
