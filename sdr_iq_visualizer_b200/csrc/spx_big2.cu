@@ -38,6 +38,7 @@ struct Big2Params {
     int hop_rows;            // hop / 256
     int lanes;
     int lag, slots;          // slots = 2 lag + 2
+    float unit;              // 1.0f (a run-time value: the role-B tile is multiplied by it, see big2_load_tile)
 };
 
 // shared memory: [staging tile 32 KB, 1024-aligned][warp-local exchange buffer][window of this column tile, [16 a][256 tid]]
@@ -153,8 +154,11 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
         const bool hold = has_next && kind == 0 && nx.ph == 1 && nx.s(lag) == s;
         mbar_wait(full_u32, parity & 1u);
         parity += 1u;
-        big2_phase_a<BIG2_TUNE>(v, tid, stage, kind == 0 ? wf_ptr : nullptr, X);
-        __syncthreads();       // the staged tile is consumed; the previous role's stores are issued, its uint8 tile complete
+        big2_load_tile(v, tid, stage, kind == 0 ? wf_ptr : nullptr, p.unit);
+        // The only block barrier of the role, placed where the warps are still aligned (they all woke on the same TMA
+        // completion): the staged tile is consumed (every value was used by a multiply above), the previous role's scratch
+        // stores are issued and its uint8 tile is complete.  The exchange through X below is warp-local (__syncwarp).
+        __syncthreads();
         if (pend_slot >= 0) {
             release(pend_slot, (parity >> 1) & 7);
             pend_slot = -1;
@@ -163,7 +167,9 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
             store_run(pend_s & 1, pend_s);
             pend_s = -1;
         }
-        if (tid == 0 && has_next && !hold) issue(nx.ph, nx.s(lag));   // refill the staging tile: overlaps the rest of this role
+        if (tid == 0 && has_next && !hold) issue(nx.ph, nx.s(lag));   // refill the staging tile: overlaps the whole transform
+        big2_dft_store<BIG2_TUNE>(v, tid, X);
+        __syncwarp();
         k2_phase_b1<4096, BIG2_TUNE>(v, tid, X, twr);
         if (kind == 0) {
             const int slot = s % slots;
@@ -289,6 +295,7 @@ int big2_launch_stream(spx_plan* pl, const void* in, long long frames, long long
     p.hop_rows = pl->cfg.hop / 256;
     p.lanes = (int)lanes;
     p.lag = lag;
+    p.unit = 1.0f;
     p.slots = slots;
     SPX_CUDA(cudaMemsetAsync(p.done, 0, (size_t)lanes * slots * sizeof(int), st));
 

@@ -255,7 +255,10 @@ def run_c5(ctx, collective="fused", rows="gather", log2_samples=30, steps=5, war
             src.free()
             out["nvlink_ingress_gbs_measured"] = round(remote / best / 1e9, 1)
             out["gather_floor_ms"] = round(best * 1e3, 3)
-            out["gather_vs_floor"] = round(out["ms_per_step"] / (best * 1e3), 3)
+            # the step can be no faster than the slower of this rank's kernels and the NVLink ingress of rank 0
+            bound = max(best * 1e3, out.get("kernel_ms_max_rank", 0.0))
+            out["gather_bound_ms"] = round(bound, 3)
+            out["gather_vs_bound"] = round(out["ms_per_step"] / bound, 3)
             out["nvlink_gbs_achieved"] = round(remote / (out["ms_per_step"] * 1e-3) / 1e9, 1)
 
     if collective == "fused":
