@@ -38,6 +38,7 @@ struct Big2Params {
     int hop_rows;            // hop / 256
     int lanes;
     int lag, slots;          // slots = 2 lag + 2
+    int rotate;              // duty rotation among the warps (env SPX_BIG2_ROTATE, default 1)
     float unit;              // 1.0f (a run-time value: the role-B tile is multiplied by it, see big2_load_tile)
 };
 
@@ -159,8 +160,9 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
         // completion): the staged tile is consumed (every value was used by a multiply above), the previous role's scratch
         // stores are issued and its uint8 tile is complete.  The exchange through X below is warp-local (__syncwarp).
         __syncthreads();
+        const int duty = (p.rotate ? (int)(parity >> 1) : 0) & 7;     // the warp that pays for this role's fence / poll
         if (pend_slot >= 0) {
-            release(pend_slot, (parity >> 1) & 7);
+            release(pend_slot, duty);
             pend_slot = -1;
         }
         if (pend_s >= 0) {
@@ -296,6 +298,8 @@ int big2_launch_stream(spx_plan* pl, const void* in, long long frames, long long
     p.lanes = (int)lanes;
     p.lag = lag;
     p.unit = 1.0f;
+    p.rotate = 1;
+    if (const char* e = getenv("SPX_BIG2_ROTATE")) p.rotate = atoi(e);
     p.slots = slots;
     SPX_CUDA(cudaMemsetAsync(p.done, 0, (size_t)lanes * slots * sizeof(int), st));
 
