@@ -443,7 +443,7 @@ def main():
         pl.close(); d_in.free(); d_wf.free()
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_sharded as bs
-        ctx = bs.Ctx(rank, world, local, dist)
+        ctx = bs.Ctx(rank, world, local, dist, strict=False)   # a failed check is reported in the line (and on stderr), loudly, not by losing the line
         block = bs.synth_block()
         lg = args.sharded_log2
         sharded = {"scaling": "strong", "n_gpus": world, "unit": "Msamples/s",
@@ -536,6 +536,10 @@ def main():
         line["sustained"] = sustained
     if sharded is not None:
         line["sharded"] = sharded
+        checks = [v.get("check", "") for v in list(sharded["c5"].values()) + [sharded["c4"]] if isinstance(v, dict)]
+        line["sharded"]["parity"] = "ok" if all(c.startswith("ok") for c in checks) else "FAILED"
+        if line["sharded"]["parity"] != "ok":
+            print("SHARDED PARITY CHECK FAILED: " + "; ".join(checks), file=sys.stderr, flush=True)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single()
     print(json.dumps(line), flush=True)

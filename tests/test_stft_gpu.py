@@ -520,3 +520,36 @@ def test_non_finite_samples_and_extreme_values(sp):
     X = oracle_rows(raw, 64, 1, "rect", fmt=1)
     assert np.abs(r.spectrum - X).max() <= 4e-6 * np.abs(X).max()
     pl.close()
+
+
+@pytest.mark.parametrize("n", [2, 4, 16, 64, 256, 1024, 4096, 8192])
+def test_stream_frame_float64_kernel_vs_numpy(sp, n):
+    """K6 (spx_stream_frame_f64): the reference's three lines (streamer.py:119-121) in float64 on the GPU, complex128 and
+    complex64 input, any power-of-two buffer up to 8192 samples: within 1e-9 dB of numpy on every bin, exact frequency
+    axis, uint8 row equal to the float64 definition except at exact ties."""
+    rng = np.random.default_rng(n)
+    x = np.rint(rng.normal(0, 300, n) + 1j * rng.normal(0, 300, n)) + 1500 * np.exp(2j * np.pi * 0.123 * np.arange(n))
+    fs, fc = 2.5e6, 9.15e8
+    f_ref, p_ref = sref.stream_frame(x, fs, fc)
+    f, p, wf = sp.stream_frame(x, fs, fc, wf_range=(0.0, 140.0))
+    np.testing.assert_array_equal(f, f_ref)
+    assert p.dtype == np.float64 and np.abs(p - p_ref).max() <= 1e-9
+    pre = (p_ref - 0.0) * 256.0 / 140.0
+    want = np.clip(np.floor(pre), 0, 255).astype(np.uint8)
+    assert np.all((wf == want) | (np.abs(pre - np.rint(pre)) < 1e-6))
+    x32 = x.astype(np.complex64)
+    _, p32 = sp.stream_frame(x32, fs, fc)
+    _, p32_ref = sref.stream_frame(x32.astype(np.complex128), fs, fc)
+    assert np.abs(p32 - p32_ref).max() <= 1e-9
+    assert np.array_equal(sp.stream_frame(np.zeros(n, complex), fs, fc)[1], np.full(n, -240.0))
+
+
+def test_copy_ceiling_probe_reports_a_plausible_rate():
+    import ctypes as C
+    from sdr_iq_visualizer_b200 import _native as nat
+    a, b = nat.pinned_empty(32 << 20, np.uint8), nat.pinned_empty(32 << 20, np.uint8)
+    a[:] = 1
+    sec = C.c_double()
+    nat.check(nat.lib().spx_copy_ceiling(0, a.ctypes.data, a.nbytes, b.ctypes.data, b.nbytes, 8 << 20, 2, C.byref(sec)))
+    gbs = a.nbytes / sec.value / 1e9
+    assert 1.0 < gbs < 200.0 and np.all(b == 0)      # the probe copies its own zeroed device buffer out

@@ -37,9 +37,10 @@ BLOCK_LOG2 = 22
 class Ctx:
     """Rank context shared with bench.py: torch.distributed is the plumbing (barriers, handles, tiny tensors)."""
 
-    def __init__(self, rank, world, local, dist):
+    def __init__(self, rank, world, local, dist, strict=True):
         from sdr_iq_visualizer_b200 import _native as nat
         self.rank, self.world, self.local, self.dist, self.nat = rank, world, local, dist, nat
+        self.strict = strict      # a failed parity check aborts (CLI, tests); bench.py records "FAILED" in its line instead
         self.lib = nat.lib()
         self.dev = local
 
@@ -233,7 +234,7 @@ def run_c5(ctx, collective="fused", rows="gather", log2_samples=30, steps=5, war
         ok = ctx.reduce_min(ok)
         out["check"] = ("ok: reduced Welch / max-hold of all %d frames and rows at every shard boundary vs the float64 checker" % F) \
             if ok > 0.5 else "FAILED"
-        if ok < 0.5:
+        if ok < 0.5 and ctx.strict:
             raise SystemExit("c5 parity check failed")
 
     if gather and collective == "fused":
@@ -364,7 +365,7 @@ def run_c4(ctx, log2_samples=24, streams=64, steps=5, warmup=2, check=True, bloc
         ok = ctx.reduce_min(ok)
         out["check"] = "ok: stream %d Welch PSD and SNR vs the float64 checker, %d feature structs gathered" % (s0, n_feats) \
             if ok > 0.5 else "FAILED"
-        if ok < 0.5:
+        if ok < 0.5 and ctx.strict:
             raise SystemExit("c4 parity check failed")
     pl.close()
     d_in.free()
