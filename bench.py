@@ -287,30 +287,45 @@ def main():
     # ---------------- device-resident leg: every launch of a step goes to the plan's compute stream
     d_in = nat.DeviceArray.from_host(host_in, dev)
     d_wf = nat.DeviceArray((F, NFFT), np.uint8, dev)
-    d_we = nat.DeviceArray((1, NFFT), np.float64, dev)
-    d_mh = nat.DeviceArray((1, NFFT), np.float32, dev)
-    d_pxx = nat.DeviceArray((NFFT,), np.float64, dev)
-    d_pdb = nat.DeviceArray((NFFT,), np.float64, dev)
-    d_we_flat = nat.DeviceView(d_we.ptr, (NFFT,), np.float64, dev)
+    # two sets of Welch-block buffers: the classifier measurements of block k run on a side stream next to the STFT of
+    # block k+1 (they are one latency-bound CTA; serialised behind the STFT kernel they were 8 % of the step)
+    d_we = [nat.DeviceArray((1, NFFT), np.float64, dev) for _ in range(2)]
+    d_mh = [nat.DeviceArray((1, NFFT), np.float32, dev) for _ in range(2)]
+    d_pxx = [nat.DeviceArray((NFFT,), np.float64, dev) for _ in range(2)]
+    d_pdb = [nat.DeviceArray((NFFT,), np.float64, dev) for _ in range(2)]
+    d_we_flat = [nat.DeviceView(w.ptr, (NFFT,), np.float64, dev) for w in d_we]
     st = pl.stream
+    side = [nat.SideStream(dev), nat.SideStream(dev)]     # one per buffer set: STFT k waits for the side work of step k-2 only
     total_timer = nat.DeviceTimer(dev, st)
     kernel_timers = [nat.DeviceTimer(dev, st) for _ in range(args.steps)]
+    step_no = [0]
 
     def device_step(ktimer):
-        # fused STFT launch (bracketed by its own CUDA events when timed), Welch finalize, classifier features
+        # fused STFT launch on the plan's stream (bracketed by its own CUDA events when timed); Welch finalize + classifier
+        # features of this block on the side stream behind it.  Buffer set b is reused two steps later: its STFT waits for
+        # the side-stream work of step k-2 through the join below.
+        b = step_no[0] & 1
+        step_no[0] += 1
+        side[b].then(st)        # the side work of step k-2 (same buffer set) precedes this STFT; step k-1's runs next to it
         if ktimer is not None:
             ktimer.start()
-        res = pl.stft(d_in, wf_rows=d_wf, welch=d_we, maxhold=d_mh, vmin=VMIN, vmax=VMAX)
+        res = pl.stft(d_in, wf_rows=d_wf, welch=d_we[b], maxhold=d_mh[b], vmin=VMIN, vmax=VMAX)
         if ktimer is not None:
             ktimer.stop()
-        pl.welch_finalize(d_we_flat, res.n_frames, FS, pxx=d_pxx, pdb=d_pdb)
-        # classifier features of this Welch block: kernel + asynchronous copy of the result struct to pinned memory,
-        # everything enqueued on the plan's stream (the host never waits inside a step; results are read after the loop)
-        return fq.enqueue(d_pdb, NFFT)
+        side[b].after(st)
+        pl.welch_finalize(d_we_flat[b], res.n_frames, FS, pxx=d_pxx[b], pdb=d_pdb[b], stream=side[b].handle)
+        # kernel + asynchronous copy of the result struct to pinned memory (the host never waits inside a step; results
+        # are read after the loop)
+        return fq[b].enqueue(d_pdb[b], NFFT), b
 
-    fq = features.FeatureQueue(1, dev, st, slots=max(args.steps, args.warmup, 1))
+    def join_side():
+        side[0].then(st)        # the timed region on `st` ends after the last blocks' measurements
+        side[1].then(st)
+
+    fq = [features.FeatureQueue(1, dev, sd_.handle, slots=max(args.steps, args.warmup, 1)) for sd_ in side]
     for _ in range(args.warmup):
         device_step(None)
+    join_side()
     sampler = ClockSampler(dev)
     if dist is not None:
         dist.barrier()
@@ -319,10 +334,11 @@ def main():
     total_timer.start()
     for i in range(args.steps):
         last_slot = device_step(kernel_timers[i])
+    join_side()
     total_timer.stop()
     dt_dev = total_timer.elapsed_ms() * 1e-3
     nat.device_sync(dev)
-    feat = fq.results(last_slot)[0]
+    feat = fq[last_slot[1]].results(last_slot[0])[0]
     kernel_ms = [t.elapsed_ms() for t in kernel_timers]
     dt_dev = barrier_max(dist, local, dt_dev)
 
@@ -340,6 +356,7 @@ def main():
         sus_timer.start()
         for _ in range(n_sus):
             device_step(None)
+        join_side()
         sus_timer.stop()
         dt_sus = sus_timer.elapsed_ms() * 1e-3
         nat.device_sync(dev)

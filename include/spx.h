@@ -101,6 +101,11 @@ SPX_API int spx_device_sync(int device);
 /* device -> device copy on `stream`; either pointer may be a peer GPU's buffer mapped with spx_ipc_open (NVLink) */
 SPX_API int spx_memcpy_d2d_async(int device, void* dst, const void* src, size_t bytes, void* stream);
 SPX_API int spx_stream_sync(int device, void* stream);
+/* side streams for callers that overlap SPX_MEM_DEVICE calls (e.g. the classifier measurements of Welch block k next to
+ * the STFT of block k+1): everything enqueued on `waiter` after the call runs after what `signaller` holds now */
+SPX_API int spx_stream_create(int device, void** stream_out);
+SPX_API int spx_stream_destroy(int device, void* stream);
+SPX_API int spx_stream_wait_stream(int device, void* waiter, void* signaller);
 
 /* Measured copy ceiling of THIS box for the end-to-end path: h2d_bytes from `host_in` and d2h_bytes into `host_out`
  * (the caller's own pinned buffers) move concurrently on two streams in `piece_bytes` pieces, nothing else running;

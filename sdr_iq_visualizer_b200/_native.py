@@ -141,6 +141,9 @@ _SIGNATURES = {
     "spx_ipc_close": (C.c_int, [C.c_int, C.c_void_p]),
     "spx_memcpy_d2d_async": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "spx_stream_sync": (C.c_int, [C.c_int, C.c_void_p]),
+    "spx_stream_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "spx_stream_destroy": (C.c_int, [C.c_int, C.c_void_p]),
+    "spx_stream_wait_stream": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "spx_copy_ceiling": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
                                    C.POINTER(C.c_double)]),
     "spx_peer_reduce": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -434,6 +437,42 @@ class DeviceTimer:
         if self._h:
             lib().spx_timer_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SideStream:
+    """A non-blocking CUDA stream owned by Python, with the one ordering primitive callers need: ``after(other)`` makes
+    this stream wait for what ``other`` (a cudaStream_t as int, or another SideStream) holds now."""
+
+    def __init__(self, device: int = 0):
+        self.device = int(device)
+        h = C.c_void_p()
+        check(lib().spx_stream_create(self.device, C.byref(h)))
+        self.handle = int(h.value)
+
+    @staticmethod
+    def _h(s):
+        return s.handle if isinstance(s, SideStream) else (s or None)
+
+    def after(self, other) -> None:
+        check(lib().spx_stream_wait_stream(self.device, self.handle, self._h(other)))
+
+    def then(self, other) -> None:
+        """``other`` waits for what this stream holds now."""
+        check(lib().spx_stream_wait_stream(self.device, self._h(other), self.handle))
+
+    def sync(self) -> None:
+        check(lib().spx_stream_sync(self.device, self.handle))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib().spx_stream_destroy(self.device, self.handle)
+            self.handle = None
 
     def __del__(self):
         try:

@@ -96,6 +96,33 @@ int spx_memcpy_d2d_async(int device, void* dst, const void* src, size_t bytes, v
     return SPX_OK;
 }
 
+int spx_stream_create(int device, void** stream_out) {
+    if (!stream_out) return spx_set_error(SPX_E_INVALID, "stream_out is NULL");
+    SPX_CUDA(cudaSetDevice(device));
+    cudaStream_t s = nullptr;
+    SPX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream_out = (void*)s;
+    return SPX_OK;
+}
+
+int spx_stream_destroy(int device, void* stream) {
+    if (!stream) return SPX_OK;
+    SPX_CUDA(cudaSetDevice(device));
+    SPX_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return SPX_OK;
+}
+
+int spx_stream_wait_stream(int device, void* waiter, void* signaller) {
+    SPX_CUDA(cudaSetDevice(device));
+    cudaEvent_t e = nullptr;
+    SPX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t r = cudaEventRecord(e, (cudaStream_t)signaller);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent((cudaStream_t)waiter, e, 0);
+    cudaEventDestroy(e);      // released once the recorded work has completed
+    if (r != cudaSuccess) return spx_set_error(SPX_E_CUDA, "spx_stream_wait_stream: %s", cudaGetErrorString(r));
+    return SPX_OK;
+}
+
 int spx_stream_sync(int device, void* stream) {
     SPX_CUDA(cudaSetDevice(device));
     SPX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

@@ -237,7 +237,7 @@ class SpectralPlan:
         return int(st.value or 0)
 
     def welch_finalize(self, welch_acc, n_frames: int, sample_rate: float, want_db: bool = True, pxx=None, pdb=None,
-                       n_streams: int = 1):
+                       n_streams: int = 1, stream: int = 0):
         """mlab.psd density and its dB from an accumulated numerator (``n_streams`` accumulators laid out
         [n_streams][nfft], one launch).  ``pxx`` / ``pdb`` may be caller buffers (same memory space as
         ``welch_acc``) to avoid an allocation per call."""
@@ -256,7 +256,7 @@ class SpectralPlan:
             pxx = DeviceArray((N,), np.float64, self.device) if pxx is None else pxx
             pdb = (DeviceArray((N,), np.float64, self.device) if want_db else None) if pdb is None else pdb
         nat.check(nat.lib().spx_welch_finalize_batch(self._h, mem, p, int(n_streams), int(n_frames), float(sample_rate),
-                                                     nat.as_ptr(pxx)[0], nat.as_ptr(pdb)[0], None))
+                                                     nat.as_ptr(pxx)[0], nat.as_ptr(pdb)[0], stream or None))
         return pxx, pdb
 
 
