@@ -21,37 +21,40 @@ namespace spx {
 enum { BIG2_N = 65536, BIG2_TILES = 16 };   // 16 column tiles / 16 row tiles of 16
 
 // ---- phase A of either role, in two halves so that the block barrier that frees the staged tile can sit between them:
-// (1) swizzled tile -> registers, times the window (role A) or a unit scale (role B): every loaded value is consumed
-//     by an arithmetic instruction here, so all shared-memory reads of the tile are complete when this returns;
-// (2) radix-16 over a -> warp-local tile X[c][17 b + k_a].
+// (1) swizzled tile -> registers, window (role A), first butterfly layer of the radix-16 over a: every loaded value is
+//     consumed by an arithmetic instruction here, so all shared-memory reads of the tile are complete when this returns;
+// (2) second layer -> warp-local tile X[c][17 b + k_a].
 // `w` (role A): this thread's 16 window * scale values, w[WS * a] (a table [16 a][256 tid] offset by tid: WS = 256; or a
-// private array: WS = 1); nullptr for role B / rect window, which multiply by `unit` (1.0f, a run-time value).
+// private array: WS = 1); nullptr for role B / rect window.
 template <int WS = 256>
-SPX_HD void big2_load_tile(float2* v, int tid, const void* stage, const float* w, float unit) {
+SPX_HD void big2_load_tile(float2* v, int tid, const void* stage, const float* w) {
     const int b = k2_b_of(tid), c = k2_c_of(tid);
     const unsigned off0 = swz128(8u * (unsigned)(16 * b + c));
     const char* st = reinterpret_cast<const char*>(stage);
 #pragma unroll
     for (int a = 0; a < 16; ++a) v[a] = *reinterpret_cast<const float2*>(st + off0 + (unsigned)a * 2048u);
+    if (w != nullptr) {
 #pragma unroll
-    for (int a = 0; a < 16; ++a) {
-        const float wa = w != nullptr ? w[WS * a] : unit;
-        v[a].x *= wa;
-        v[a].y *= wa;
+        for (int a = 0; a < 16; ++a) {
+            const float wa = w[WS * a];
+            v[a].x *= wa;
+            v[a].y *= wa;
+        }
     }
+    dft16_layer1(v);
 }
-template <int TUNE>
 SPX_HD void big2_dft_store(float2* v, int tid, float2* X) {
     using G = Stft2Geom<4096>;
-    k2_dft16<TUNE>(v);
+    dft16_fma_layer2(v);
     float2* dst = X + G::XS * k2_c_of(tid) + 17 * k2_b_of(tid);
 #pragma unroll
     for (int k = 0; k < 16; ++k) dst[k] = v[k];
 }
 template <int TUNE, int WS = 256>
 SPX_HD void big2_phase_a(float2* v, int tid, const void* stage, const float* w, float2* X) {
-    big2_load_tile<WS>(v, tid, stage, w, 1.0f);
-    big2_dft_store<TUNE>(v, tid, X);
+    static_assert((TUNE & TUNE_FMADFT) != 0, "K2v2 uses the FMA-form radix-16");
+    big2_load_tile<WS>(v, tid, stage, w);
+    big2_dft_store(v, tid, X);
 }
 
 // sample index of register a of phase-A thread tid in column tile g (host: builds the [16 g][16 a][256 tid] window table)

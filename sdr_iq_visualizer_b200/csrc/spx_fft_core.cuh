@@ -158,11 +158,20 @@ SPX_HD float2 cfma(float2 b, float s, float2 a) {   // a + s * b
 }
 #define SPX_T1 0.41421356237309504880f   // tan(pi/8)
 
-SPX_HD void dft16_fma(float2* v) {
+// first layer (four radix-4 butterflies over stride 4): consumes every input once -- K2v2 runs it in front of its block
+// barrier so that all shared-memory reads of the staged tile are complete there
+SPX_HD void dft16_layer1(float2* v) {
     dft4(v[0], v[4], v[8], v[12]);
     dft4(v[1], v[5], v[9], v[13]);
     dft4(v[2], v[6], v[10], v[14]);
     dft4(v[3], v[7], v[11], v[15]);
+}
+SPX_HD void dft16_fma_layer2(float2* v);
+SPX_HD void dft16_fma(float2* v) {
+    dft16_layer1(v);
+    dft16_fma_layer2(v);
+}
+SPX_HD void dft16_fma_layer2(float2* v) {
     // c' = 0: no twiddles
     dft4(v[0], v[1], v[2], v[3]);
     {   // c' = 1: y1 = v5 W^1 = C1 (x + t y, y - t x);  y2 = v6 W^2 = H (x + y, y - x);  y3 = v7 W^3 = C1 * (-i) (x - t y, y + t x)

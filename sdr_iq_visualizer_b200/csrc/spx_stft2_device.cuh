@@ -100,6 +100,20 @@ SPX_HD void k2_phase_b1(float2* v, int tid, const float2* X, const TwRegs<N>& tw
     pass_twiddle_regs<N, 1>(v, twr);
     k2_dft16<TUNE>(v);
 }
+// same, with the 15 x 16 twiddles W_256^{b k_a} read from a shared-memory table tw256[(b - 1) * 16 + k_a] instead of being
+// rebuilt from six register bases every frame: 15 conflict-free LDS.64 (both half-warps read the same 16 entries) against
+// 9 complex products and 12 registers (used by K2v2, whose two roles leave the load/store pipe at 25 %)
+template <int N, int TUNE = 0>
+SPX_HD void k2_phase_b1_tab(float2* v, int tid, const float2* X, const float2* tw256) {
+    using G = Stft2Geom<N>;
+    const int ka = k2_ka_of(tid);
+    const float2* src = X + G::XS * k2_cb_of(tid) + ka;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) v[b] = src[17 * b];
+#pragma unroll
+    for (int b = 1; b < 16; ++b) v[b] = cmul(v[b], tw256[(b - 1) * 16 + ka]);
+    k2_dft16<TUNE>(v);
+}
 template <int N>
 SPX_HD void k2_phase_b2(const float2* v, int tid, float2* X) {
     using G = Stft2Geom<N>;

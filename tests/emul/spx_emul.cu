@@ -272,8 +272,8 @@ extern "C" int spx_emul_big2(const void* in, long long n_samples, int hop, const
     const float2* x = reinterpret_cast<const float2*>(in);
     if (tune) return acc ? emul_big2<true, TUNE_FMADFT | TUNE_QFMA>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold)
                          : emul_big2<false, TUNE_FMADFT | TUNE_QFMA>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold);
-    return acc ? emul_big2<true, 0>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold)
-               : emul_big2<false, 0>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold);
+    return acc ? emul_big2<true, TUNE_FMADFT>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold)
+               : emul_big2<false, TUNE_FMADFT>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold);
 }
 
 // plan introspection for the tests
