@@ -21,6 +21,17 @@ tmap_encode_fn tmap_encoder() {
 }
 
 int launch_stft2(StftLaunch& L) {
+    if (L.variant == 23) {   // strip staging of overlapping frames (experiment; N = 4096, hop = N/2 or N/4), else the default
+        int rc = SPX_OK;
+        if (launch_stft2_strip<2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L, &rc)) return rc;
+        return launch_stft2_n<4096, 2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L);
+    }
+    if (L.variant == 0 && L.nfft == 4096 && L.in_fmt == FMT_CF32 && L.p.hop == 1024) {
+        // measured (profiles/r02_strip_staging_sweep.jsonl): strip staging wins 3 % on cf32 at 75 % overlap (the frame is
+        // 32 KB, three quarters of it already in shared memory), is neutral for ci16 and at 50 % overlap -- used only here
+        int rc = SPX_OK;
+        if (launch_stft2_strip<2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L, &rc)) return rc;
+    }
     if (L.variant == 22 || L.variant == 0) {   // default: FMA-form DFTs + uint8 index on the FMA / ALU pipes instead of F2I (XU)
         switch (L.nfft) {
             case 1024: return launch_stft2_n<1024, 2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L);

@@ -86,6 +86,41 @@ SPX_HD void k2_phase_a(float2* v, int tid, const void* stage, const float* wtab,
     for (int k = 0; k < 16; ++k) dst[k] = v[k];
 }
 
+// ---- phase A with STRIP STAGING (N = 4096, hop = N / R, R = 2 or 4): the staging buffer is a ring of R hop-sized blocks; a
+// frame inside a chunk only copies its newest block (1/R of the frame), the other R - 1 blocks are still there from its
+// predecessors.  Logical block j of chunk-frame fi sits in ring slot (fi + j) mod R; `ring0` = fi mod R.
+template <int FMT, int R, int TUNE>
+SPX_HD void k2_phase_a_strip(float2* v, int tid, const void* stage, int ring0, const float* wtab, float2* X) {
+    using G = Stft2Geom<4096>;
+    constexpr unsigned ELT = FMT == FMT_CF32 ? 8u : 4u;
+    constexpr unsigned STEP = 256u * ELT;            // bytes between registers a and a + 1 (a multiple of 1024)
+    constexpr int APB = 16 / R;                      // registers per block
+    constexpr unsigned BLK = APB * STEP;             // bytes per ring block (= hop samples)
+    const int b = k2_b_of(tid), c = k2_c_of(tid);
+    const char* st = reinterpret_cast<const char*>(stage) + swz128(ELT * (unsigned)(16 * b + c));
+    unsigned boff[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) boff[j] = (unsigned)((j + ring0) & (R - 1)) * BLK;
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+        const unsigned off = boff[a / APB] + (unsigned)(a % APB) * STEP;
+        if (FMT == FMT_CF32) v[a] = *reinterpret_cast<const float2*>(st + off);
+        else                 v[a] = ci16_to_f2<TUNE>(*reinterpret_cast<const unsigned int*>(st + off));
+    }
+    if (wtab != nullptr) {
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+            const float w = a < 8 ? wtab[a * G::T + tid] : wtab[(15 - a) * G::T + (G::T - 1 - tid)];
+            v[a].x *= w;
+            v[a].y *= w;
+        }
+    }
+    k2_dft16<TUNE>(v);
+    float2* dst = X + G::XS * c + 17 * b;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dst[k] = v[k];
+}
+
 // ---- phase B: radix-16 over b for (k_a, c); B1 = load + twiddle + DFT, B2 = store (a __syncwarp between them: the
 // column tile is overwritten in place with Y_c[k_a + 16 k_b] at X[c][k_a + 16 k_b])
 SPX_HD int k2_ka_of(int tid) { return tid & 15; }

@@ -117,6 +117,91 @@ __global__ void __launch_bounds__(256, OCC) stft2_kernel(const StftParams p, con
     }
 }
 
+// ------------------------------------------------------------------ strip-staging variant (experiment, variant 23)
+// N = 4096, hop = N / R: only the newest hop block of a frame crosses L2 -> shared memory (north_star: "TMA /
+// shared-memory staging of overlapping frames").  Same arithmetic and data flow as stft2_kernel otherwise.
+template <int FMT, bool ACC, int R, int OCC, int TUNE>
+__global__ void __launch_bounds__(256, OCC) stft2_strip_kernel(const StftParams p, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int N = 4096;
+    using C = Stft2Cfg<N, FMT>;
+    using G = Stft2Geom<N>;
+    constexpr int ELT = FMT == FMT_CF32 ? 8 : 4;
+    constexpr unsigned BLK = C::FRAME_BYTES / R;
+    extern __shared__ unsigned char smem_raw2[];
+    __shared__ unsigned long long mbar;
+    const int tid = threadIdx.x;
+    const unsigned raw_u32 = smem_u32(smem_raw2);
+    unsigned char* base = smem_raw2 + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+    unsigned char* stage = base;
+    float2* X0 = reinterpret_cast<float2*>(base + C::FRAME_BYTES);
+    float2* X1 = X0 + G::X_F2;
+    float* wtab = nullptr;
+    if (p.win != nullptr) {
+        wtab = reinterpret_cast<float*>(base + C::FRAME_BYTES + 2 * C::X_BYTES);
+        k2_build_window<N>(wtab, p.win, tid);
+    }
+    const unsigned bar_u32 = smem_u32(&mbar), stage_u32 = smem_u32(stage);
+    if (tid == 0) mbar_init(bar_u32, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    TwRegs<N> twr;
+    tw_regs_load_pass<N, 1>(twr, k2_ka_of(tid), p.tw);
+    tw_regs_load_pass<N, 2>(twr, tid, p.tw);
+    StftAcc<ACC> acc;
+    acc.reset();
+
+    // elected thread: copy what frame `c` still lacks -- the whole frame (R blocks) at the start of a chunk, else its newest block
+    auto fetch = [&](const FrameCursor& c) {
+        const long long row0 = (c.sample0(p) * ELT) >> 7;
+        if (c.fi == 0) {
+            mbar_expect_tx(bar_u32, C::FRAME_BYTES);
+#pragma unroll
+            for (int j = 0; j < R; ++j) tma_load_rows(stage_u32 + j * BLK, &tmap, (int)(row0 + j * (BLK / 128)), bar_u32);
+        } else {
+            mbar_expect_tx(bar_u32, BLK);
+            tma_load_rows(stage_u32 + (unsigned)((c.fi - 1) & (R - 1)) * BLK, &tmap, (int)(row0 + (R - 1) * (BLK / 128)), bar_u32);
+        }
+    };
+
+    const unsigned n_workers = gridDim.x;
+    FrameCursor cur;
+    cur.seek(p, blockIdx.x);
+    unsigned parity = 0;
+    if (cur.valid && tid == 0) fetch(cur);
+    float2 v[16];
+    while (cur.valid) {
+        const long long row = cur.row();
+        const bool last_in_chunk = cur.fi + 1 == cur.nf;
+        const unsigned this_stream = cur.stream;
+        FrameCursor nxt = cur;
+        if (!last_in_chunk) nxt.fi = cur.fi + 1;
+        else nxt.seek(p, cur.chunk + n_workers);
+        float2* X = parity ? X1 : X0;
+        mbar_wait(bar_u32, parity);
+        k2_phase_a_strip<FMT, R, TUNE>(v, tid, stage, cur.fi & (R - 1), wtab, X);
+        __syncwarp();
+        k2_phase_b1<N, TUNE>(v, tid, X, twr);
+        __syncwarp();
+        k2_phase_b2<N>(v, tid, X);
+        __syncthreads();
+        if (nxt.valid && tid == 0) fetch(nxt);
+        k2_phase_c<N, ACC, true, TUNE>(v, tid, X, p, row, p.tw, twr, acc);
+        parity ^= 1u;
+        if constexpr (ACC) {
+            if (last_in_chunk) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const long long o = (long long)this_stream * N + acc_pos<N>(tid, i);
+                    flush_acc(p.welch_acc, p.maxhold, o, acc.sum[i], acc.mx[i], p.sys_atomics);
+                }
+                acc.reset();
+            }
+        }
+        cur = nxt;
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -179,6 +264,69 @@ int launch_stft2_inst(StftLaunch& L) {
     kern<<<(unsigned)grid, C::THREADS, C::SMEM, L.stream>>>(L.p, tmap);
     SPX_CUDA(cudaGetLastError());
     return SPX_OK;
+}
+
+template <int FMT, bool ACC, int R, int OCC, int TUNE>
+int launch_stft2_strip_inst(StftLaunch& L) {
+    constexpr int N = 4096;
+    using C = Stft2Cfg<N, FMT>;
+    auto kern = stft2_strip_kernel<FMT, ACC, R, OCC, TUNE>;
+    static int occ_cache[64] = {0};
+    int dev = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    int occ = occ_cache[dev & 63];
+    if (occ == 0) {
+        SPX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, C::SMEM));
+        if (occ < 1) return spx_set_error(SPX_E_CUDA, "stft2 strip kernel does not fit on an SM");
+        occ_cache[dev & 63] = occ;
+    }
+    // long chunks (the strip only pays inside a chunk): one chunk per worker and stream where possible, <= 256 frames
+    const long long workers_max = (long long)L.sm_count * occ;
+    const long long F = L.p.frames_per_stream;
+    long long per_worker = (L.total_frames + workers_max - 1) / workers_max;
+    long long fpc = per_worker < 1 ? 1 : per_worker;
+    if (fpc > 256) {
+        const long long waves = (per_worker + 255) / 256;
+        fpc = (per_worker + waves - 1) / waves;
+    }
+    if (fpc > F) fpc = F;
+    const long long cps = (F + fpc - 1) / fpc;
+    L.p.frames_per_chunk = (int)fpc;
+    L.p.chunks_per_stream = (int)cps;
+    L.p.total_chunks = cps * L.p.n_streams;
+    long long grid = L.p.total_chunks < workers_max ? L.p.total_chunks : workers_max;
+    if (grid < 1) grid = 1;
+    const long long elt = FMT == FMT_CF32 ? 8 : 4;
+    const long long last_sample = (long long)(L.p.n_streams - 1) * L.p.stream_stride + (F - 1) * L.p.hop + N;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {32, (cuuint64_t)((last_sample * elt) / 128)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {32, C::ROWS / R};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = tmap_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(L.p.in), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return spx_set_error(SPX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    kern<<<(unsigned)grid, 256, C::SMEM, L.stream>>>(L.p, tmap);
+    SPX_CUDA(cudaGetLastError());
+    return SPX_OK;
+}
+
+// variant 23: strip staging, N = 4096 and hop = N/2 or N/4 only (false: not applicable, the caller takes the default kernel)
+template <int OCC, int TUNE>
+bool launch_stft2_strip(StftLaunch& L, int* rc) {
+    if (L.nfft != 4096 || (L.p.hop != 1024 && L.p.hop != 2048)) return false;
+    const bool acc = L.p.welch_acc != nullptr || L.p.maxhold != nullptr;
+    const bool cf = L.in_fmt == FMT_CF32;
+    if (L.p.hop == 1024) {
+        *rc = cf ? (acc ? launch_stft2_strip_inst<FMT_CF32, true, 4, OCC, TUNE>(L) : launch_stft2_strip_inst<FMT_CF32, false, 4, OCC, TUNE>(L))
+                 : (acc ? launch_stft2_strip_inst<FMT_CI16, true, 4, OCC, TUNE>(L) : launch_stft2_strip_inst<FMT_CI16, false, 4, OCC, TUNE>(L));
+    } else {
+        *rc = cf ? (acc ? launch_stft2_strip_inst<FMT_CF32, true, 2, OCC, TUNE>(L) : launch_stft2_strip_inst<FMT_CF32, false, 2, OCC, TUNE>(L))
+                 : (acc ? launch_stft2_strip_inst<FMT_CI16, true, 2, OCC, TUNE>(L) : launch_stft2_strip_inst<FMT_CI16, false, 2, OCC, TUNE>(L));
+    }
+    return true;
 }
 
 template <int N, int OCC, int TUNE>

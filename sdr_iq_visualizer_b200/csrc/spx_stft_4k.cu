@@ -5,6 +5,7 @@ namespace spx {
 int launch_stft_4k(StftLaunch& L) {
     switch (L.variant) {
         case 0:    // default = K1v2 with FMA-form DFTs and the FMA-pipe colormap index (variant 22); K1 when frames are not 128-byte aligned
+        case 23:   // + strip staging of overlapping frames (experiment)
         case 22:   // + colormap index without the XU pipe
         case 21:   // K1v2 + FMA-form radix-16 DFTs
         case 20:   // K1v2: warp-local first exchange, one barrier per frame

@@ -553,3 +553,25 @@ def test_copy_ceiling_probe_reports_a_plausible_rate():
     nat.check(nat.lib().spx_copy_ceiling(0, a.ctypes.data, a.nbytes, b.ctypes.data, b.nbytes, 8 << 20, 2, C.byref(sec)))
     gbs = a.nbytes / sec.value / 1e9
     assert 1.0 < gbs < 200.0 and np.all(b == 0)      # the probe copies its own zeroed device buffer out
+
+
+@pytest.mark.parametrize("hop,fmt,frames", [(1024, 1, 3000), (1024, 0, 1500), (2048, 0, 2000), (2048, 1, 777), (1024, 1, 5)])
+def test_k1v2_strip_staging_variant_is_bit_identical(sp, hop, fmt, frames):
+    """Variant 23 (ring of hop blocks in the staging buffer: a frame inside a chunk copies only its newest block): same
+    arithmetic as the default kernel, so every output is bit-identical; chunk starts (whole-frame copies), ring
+    wrap-around and short inputs are all exercised."""
+    n = 4096
+    L = n + hop * (frames - 1) + 3
+    xc = sref.synth_iq(L, seed=hop + frames)
+    x = sref.to_ci16(xc) if fmt else xc.astype(np.complex64)
+    vmin, vmax = (0.0, 130.0) if fmt else (-60.0, 60.0)
+    a = sp.SpectralPlan(n, hop, "hann", fmt, variant=23)
+    b = sp.SpectralPlan(n, hop, "hann", fmt, variant=22)
+    ra = a.stft(x, db_rows=True, wf_rows=True, welch=True, maxhold=True, vmin=vmin, vmax=vmax)
+    rb = b.stft(x, db_rows=True, wf_rows=True, welch=True, maxhold=True, vmin=vmin, vmax=vmax)
+    assert ra.n_frames == rb.n_frames == frames
+    np.testing.assert_array_equal(ra.db_rows, rb.db_rows)
+    np.testing.assert_array_equal(ra.wf_rows, rb.wf_rows)
+    np.testing.assert_array_equal(ra.maxhold, rb.maxhold)
+    np.testing.assert_allclose(ra.welch_acc, rb.welch_acc, rtol=1e-12)     # fp64 atomics: the order of the flushes may differ
+    a.close(); b.close()
