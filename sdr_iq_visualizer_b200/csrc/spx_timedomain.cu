@@ -21,6 +21,16 @@ struct HistGrid {
     int bins;
 };
 
+// Per-launch constants of the shared-memory histogram kernel, built on the host (as kernel parameters they are constant-bank
+// operands; derived inside the kernel the compiler rebuilds them per sample to save registers).
+struct HistConst {
+    float fa, fb;         // bin estimate u = fa * x + fb = (x * scale - start) / step - 1/2
+    float neg_center;     // -(bins - 1) / 2
+    float half_bins;      // bins / 2
+    int idx_bias;         // 0x4B400000 * (bins + 1)
+    int swz_mask;         // 31 when every table row starts on a 32-word boundary (bins % 64 == 0), else 0
+};
+
 __device__ __forceinline__ double edge_of(const HistGrid& g, int i) {
     return i >= g.bins ? g.stop : __dadd_rn(__dmul_rn((double)i, g.step), g.start);
 }
@@ -105,117 +115,236 @@ __global__ void __launch_bounds__(256) hist2d_kernel(const void* __restrict__ in
 // Shared-memory privatised variant (north_star: "a shared-memory I/Q 2-D histogram for the constellation view"), used
 // when bins^2 16-bit counters fit in shared memory (bins <= 320; 128 KB for 256 x 256).  Real constellations pile up
 // on a few thousand bins, and RED.ADD on the same L2 sectors from every SM serialises (ncu: 261 us for 2^24 samples with
-// the global-atomic kernel above, DRAM at 6 %).  Here a CTA counts a chunk of <= 65 528 samples into packed 16-bit
-// counters in shared memory (two per word, ATOMS.ADD of 1 or 1<<16 -- a chunk cannot overflow a 16-bit counter), then
-// adds its non-zero counters to the global table: ~8x fewer global atomics, spread out in time.
+// the global-atomic kernel above, DRAM at 6 %).  Here every CTA keeps ONE table of packed 16-bit counters in shared memory
+// for its whole share of the input (two per word, ATOMS.ADD of 1 or 1<<16):
+//   * the input is walked in epochs of <= 57 344 samples; between two epochs the CTA scans its table and moves every
+//     counter that has reached 2^13 to the global table (RED, rare), so a counter starts an epoch below 2^13 and cannot wrap;
+//   * at the end the table is written as it is (packed, coalesced stores) to the CTA's private slice of `tabs`, and
+//     hist_merge_kernel adds the slices up -- no atomics on the way out.  Round 2 measured why: flushing each 65 528-sample
+//     chunk with RED put ~5 M atomics on one L2-resident table (92-141 G/s, tools/micro/atom_mix.cu), 50 of the 58 us;
+//     the shared-memory atomics themselves run at 2.5-4.8 per clock and SM (12-23 us for 2^24 samples).
+//   * `tabs == nullptr` (a handful of CTAs): non-zero counters go straight to the global table with RED.
+// Neighbouring floats (finite, non-NaN arguments).
+__device__ __forceinline__ float float_up(float x) {
+    if (x == 0.f) return __int_as_float(1);
+    const int b = __float_as_int(x);
+    return __int_as_float(x > 0.f ? b + 1 : b - 1);
+}
+__device__ __forceinline__ float float_down(float x) { return -float_up(-x); }
+
 template <int FMT>
 __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restrict__ in, long long n, double scale, HistGrid g,
-                                                           unsigned int* __restrict__ hist, int vec_ok, int chunk) {
-    extern __shared__ unsigned int sh[];
+                                                           unsigned int* __restrict__ hist, int vec_ok, long long span,
+                                                           unsigned int* __restrict__ tabs, int tab_stride, HistConst hc) {
+    extern __shared__ __align__(16) unsigned int sh[];
     constexpr int SPV = FMT == SPX_FMT_CF32 ? 2 : 4;   // samples per 16-byte vector
-    constexpr int U = 4;
-    const int bins = g.bins, nb2 = bins * bins, words = (nb2 + 1) / 2;
-    // numpy's edge table in shared memory (behind the counters): the exact comparisons become two 8-byte loads instead
-    // of int->double conversions and double multiplies per component
-    double* edges = reinterpret_cast<double*>(sh + ((words + 1) & ~1));
-    for (int i = threadIdx.x; i <= bins; i += blockDim.x) edges[i] = edge_of(g, i);
-    const double start = g.start, stop = g.stop;
-    const float start_f = (float)g.start, inv_step_f = (float)g.inv_step, scale_f = (float)scale;
-    const bool unit_scale = scale == 1.0;
+    constexpr int U = FMT == SPX_FMT_CF32 ? 4 : 2;     // vectors per thread and batch: 8 samples, 8192 per CTA
+    constexpr int STEP = 1024 * U;                     // vectors per CTA and batch (the launch uses 1024 threads)
+    constexpr int EPOCH_BATCHES = 7;                   // 57 344 samples between two scans for hot counters: 8191 + 57 344 = 65 535
+    constexpr int EPOCH_SCALAR = 57344;
+    constexpr unsigned HOT = 0xE000E000u;              // a counter >= 2^13 (either half of a word)
+    const int tid = threadIdx.x;
+    const int bins = g.bins, nb2 = bins * bins, words = (nb2 + 1) / 2, quads = (words + 3) / 4;
+    uint4* sh4 = reinterpret_cast<uint4*>(sh);
+    // The exact decision, in the units of the raw input: thr[i] = the smallest float x whose value v = (double)x * scale
+    // reaches numpy's edge i (v >= e_i  <=>  x >= thr[i], the product is monotone in x for scale > 0), thr[bins + 1] = the
+    // largest x with v <= stop.  Built once per CTA from the float64 edges; comparing a sample against two neighbouring
+    // thresholds settles its bin exactly, in float, with two shared-memory loads.
+    float* thr = reinterpret_cast<float*>(sh + 4 * quads);
+    for (int i = tid; i <= bins + 1; i += 1024) {
+        const double e = i <= bins ? edge_of(g, i) : g.stop;
+        float x = (float)(e / scale);
+        if (i <= bins) {
+            while ((double)x * scale >= e && x > -3.0e38f) x = float_down(x);
+            while ((double)x * scale < e && x < 3.0e38f) x = float_up(x);
+        } else {
+            while ((double)x * scale <= e && x < 3.0e38f) x = float_up(x);
+            while ((double)x * scale > e && x > -3.0e38f) x = float_down(x);
+        }
+        thr[i] = x;
+    }
+    for (int q = tid; q < quads; q += 1024) sh4[q] = make_uint4(0u, 0u, 0u, 0u);
     // the swizzle needs every row to start on a 32-word boundary (bins a multiple of 64); otherwise it is switched off
-    const int swz_mask = (bins % 64 == 0) ? 31 : 0;
-    // float estimate of the bin (at most one off), settled exactly against the float64 edges
-    auto bin_tab = [&](float f, double v) -> int {
-        int b = __float2int_rd((f * scale_f - start_f) * inv_step_f);
-        b = max(0, min(b, bins - 1));
-        b -= (v < edges[b]) ? 1 : 0;
+    const int swz_mask = hc.swz_mask;
+    // Bin estimate u = (v - start)/step - 1/2 as ONE fma in float (constants rounded from float64): its error is below
+    // 4e-5 bins for bins <= 320 (|u| <= 160: half an ulp of the product, of the constant and of the result, 1.5e-5 each
+    // at most).  rint(u) through the 1.5 * 2^23 constant: when u is farther than HIST_EPS from a half-integer, i.e.
+    // (v - start)/step is farther than HIST_EPS from an edge, rint(u) IS the bin; otherwise the exact float64 comparison
+    // against numpy's edges decides.  Out-of-range, huge, infinite and NaN estimates give an integer outside [0, bins)
+    // (the bit pattern of u + 1.5 * 2^23 is below or far above the constant's) and are dropped, as numpy does.
+    // I and Q go through the four arithmetic steps as one packed pair (FFMA2 / FADD2).
+    constexpr float HIST_EPS = 2e-4f, MAGIC = 12582912.0f;
+    constexpr int MAGIC_BITS = 0x4B400000;
+    const float2 fa2 = make_float2(hc.fa, hc.fa), fb2 = make_float2(hc.fb, hc.fb), mg2 = make_float2(MAGIC, MAGIC), nmg2 = make_float2(-MAGIC, -MAGIC),
+                 neg2 = make_float2(-1.f, -1.f);
+    unsigned sh_base = (unsigned)__cvta_generic_to_shared(sh);
+    asm volatile("" : "+r"(sh_base));   // keep the base in a register (otherwise it is rebuilt from SR_CgaCtaId per sample)
+    // range test on the estimate itself: rint(u) in [0, bins) <=> |u - (bins - 1)/2| < bins/2 away from the two outer edges
+    // (both constants exact in float; at the outer edges the exact path decides)
+    const float2 nctr2 = make_float2(hc.neg_center, hc.neg_center);
+    const float half_bins = hc.half_bins;
+    const int idx_bias = hc.idx_bias;   // (bits(m.x) * bins + bits(m.y)) - idx_bias = bi * bins + bq  (mod 2^32)
+    // exact bin of raw component x (or -1: outside [start, stop], NaN); `est` is at most one bin off for values in range and
+    // arbitrary (clamped) for far outliers, which fail the range test
+    auto settle = [&](float x, int est) -> int {
+        int b = max(0, min(est, bins - 1));
+        b -= (x < thr[b]) ? 1 : 0;
         b = max(b, 0);
-        b += (v >= edges[b + 1] && b < bins - 1) ? 1 : 0;
-        return (v >= start && v <= stop) ? b : -1;
+        b += (x >= thr[b + 1] && b < bins - 1) ? 1 : 0;
+        return (x >= thr[0] && x <= thr[bins + 1]) ? b : -1;
     };
-    // Fast path: when the float estimate t = (v - start)/step sits at least EPS bins away from every edge, floor(t) IS
-    // the bin (the float evaluation of t is off by < 1e-4 bins for bins <= 320: three roundings of relative size
-    // 2^-24 on magnitudes <= bins/2); only the ~0.4 % of components within EPS of an edge, and everything outside
-    // the range, go through the exact float64 comparison against numpy's edge table.
-    constexpr float EPS = 2e-3f;
-    const float bins_f = (float)bins;
-    // nearest integer and distance to it with the 1.5*2^23 magic constant (FADD only, no XU conversions); t < 2^22
-    auto split = [&](float t, int& b, bool& sure) {
-        const float m = t + 12582912.0f;
-        const float rn = m - 12582912.0f;              // rint(t)
-        const float d = t - rn;                        // in [-0.5, 0.5]
-        b = (__float_as_int(m) - 0x4B400000) - (d < 0.f ? 1 : 0);   // floor(t)
-        sure = fabsf(d) > EPS && t > EPS && t < bins_f - EPS;
-    };
-    auto count_f = [&](float fr, float fi) {
-        const float ti = (fr * scale_f - start_f) * inv_step_f, tq = (fi * scale_f - start_f) * inv_step_f;
-        int bi, bq;
-        bool si, sq;
-        split(ti, bi, si);
-        split(tq, bq, sq);
-        if (!(si && sq)) {
-            const double re = unit_scale ? (double)fr : (double)fr * scale, im = unit_scale ? (double)fi : (double)fi * scale;
-            bi = bin_tab(fr, re);
-            bq = bin_tab(fi, im);
-            if (bi < 0 || bq < 0) return;
+    auto count_f = [&](float2 f) {
+        const float2 u = __ffma2_rn(f, fa2, fb2);
+        const float2 m = __fadd2_rn(u, mg2);
+        const float2 d = __ffma2_rn(__fadd2_rn(m, nmg2), neg2, u);            // u - rint(u), exact, in [-0.5, 0.5]
+        const float2 c = __fadd2_rn(u, nctr2);
+        int idx = __float_as_int(m.x) * bins + __float_as_int(m.y) - idx_bias;
+        int swz = __float_as_int(m.x) & swz_mask;                              // = bi & swz_mask: the low bits of MAGIC_BITS are 0
+        bool ok = fabsf(c.x) < half_bins && fabsf(c.y) < half_bins;            // two compares, not fmaxf: NaN must fail
+        if (fmaxf(fabsf(d.x), fabsf(d.y)) >= 0.5f - HIST_EPS) {                // near an edge: settle both exactly
+            const int bi = settle(f.x, __float_as_int(m.x) - MAGIC_BITS), bq = settle(f.y, __float_as_int(m.y) - MAGIC_BITS);
+            ok = (bi | bq) >= 0;
+            idx = bi * bins + bq;
+            swz = bi & swz_mask;
         }
         // Bank swizzle.  With idx = bi * bins + bq the bank of a counter depends on bq alone (bins/2 words per row is a
         // multiple of 32 for 256 bins), and a constellation cluster is ~15 bins wide: the 32 lanes of a warp fell on ~8
         // banks (ncu: 46.8 % of the shared wavefronts were conflicts).  XOR-ing the word index with the row number spreads
-        // a cluster over all banks; it is a bijection inside each aligned group of 32 words, undone by the flush below.
-        const int idx = bi * bins + bq;
-        atomicAdd(&sh[(idx >> 1) ^ (bi & swz_mask)], 1u << (16 * (idx & 1)));
+        // a cluster over all banks; it is a bijection inside each aligned group of 32 words, undone by hist_merge_kernel.
+        // (Integer multiply-adds instead of shifts / selects: the FMA pipe has twice the ALU pipe's rate.)
+        unsigned int val, addr;
+        asm volatile("mad.lo.u32 %0, %1, 65535, 1;" : "=r"(val) : "r"((unsigned)idx & 1u));
+        asm volatile("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"((unsigned)((idx >> 1) ^ swz)), "r"(sh_base));
+        if (ok) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
     };
-    const uint4* vin = reinterpret_cast<const uint4*>(in);
-    for (long long c = blockIdx.x; c * chunk < n; c += gridDim.x) {
-        for (int w = threadIdx.x; w < words; w += blockDim.x) sh[w] = 0u;
-        __syncthreads();
-        const long long s0 = c * chunk, s1 = (s0 + chunk < n) ? s0 + chunk : n;
-        long long done = s0;
-        if (vec_ok) {   // chunk is a multiple of 8 samples, so s0 is vector aligned
-            const long long v_lo = s0 / SPV, v_hi = s1 / SPV;
-            for (long long v0 = v_lo + threadIdx.x; v0 < v_hi; v0 += (long long)blockDim.x * U) {
-                uint4 wv[U];
+    auto count_vec = [&](const uint4& wv) {
+        if (FMT == SPX_FMT_CF32) {
+            count_f(make_float2(__uint_as_float(wv.x), __uint_as_float(wv.y)));
+            count_f(make_float2(__uint_as_float(wv.z), __uint_as_float(wv.w)));
+        } else {
+            const unsigned int q[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const long long vi = v0 + (long long)u * blockDim.x;
-                    wv[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (vi < v_hi)
-                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(wv[u].x), "=r"(wv[u].y), "=r"(wv[u].z), "=r"(wv[u].w) : "l"(vin + vi));
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (v0 + (long long)u * blockDim.x >= v_hi) break;
-                    const unsigned int q[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
-                    if (FMT == SPX_FMT_CF32) {
-                        count_f(__uint_as_float(q[0]), __uint_as_float(q[1]));
-                        count_f(__uint_as_float(q[2]), __uint_as_float(q[3]));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) count_f((float)(short)(q[k] & 0xffffu), (float)(short)(q[k] >> 16));
-                    }
-                }
-            }
-            done = v_hi * SPV;
+            for (int k = 0; k < 4; ++k) count_f(make_float2((float)(short)(q[k] & 0xffffu), (float)(short)(q[k] >> 16)));
         }
-        for (long long i = done + threadIdx.x; i < s1; i += blockDim.x) {   // tail, or the whole chunk when unaligned
+    };
+    auto unswizzled = [&](int w) { return swz_mask ? (w ^ ((2 * w / bins) & swz_mask)) : w; };   // row = 2 w / bins
+    // Between two epochs: every counter that has reached 2^13 moves to the global table, so no counter can wrap in the
+    // next epoch (< 2^13 at its start, <= 57 344 increments).  All threads of the CTA call this.
+    auto move_hot_counters = [&]() {
+        __syncthreads();
+        for (int q = tid; q < quads; q += 1024) {
+            const uint4 v4 = sh4[q];
+            if (((v4.x | v4.y | v4.z | v4.w) & HOT) == 0u) continue;
+            const unsigned int vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int v = vv[k];
+                if ((v & HOT) == 0u) continue;
+                const int wo = unswizzled(4 * q + k);
+                unsigned int keep = v;
+                if (v & (HOT & 0xffffu)) { atomicAdd(hist + 2 * wo, v & 0xffffu); keep &= 0xffff0000u; }
+                if (v & (HOT & 0xffff0000u)) { atomicAdd(hist + 2 * wo + 1, v >> 16); keep &= 0x0000ffffu; }
+                sh[4 * q + k] = keep;
+            }
+        }
+        __syncthreads();
+    };
+    __syncthreads();
+    // this CTA's share of the input: [s0, s1), s0 a multiple of 8 samples
+    const long long s0 = (long long)blockIdx.x * span, s1 = (s0 + span < n) ? s0 + span : n;
+    long long done = s0;
+    if (vec_ok && s0 < s1) {
+        // Software pipeline over batches of U vectors per thread: the loads of batch k + 1 are in flight while batch k is
+        // counted (and while the hot-counter scan runs), ld.global.nc without L1 allocation.
+        const long long v_lo = s0 / SPV, v_hi = s1 / SPV;
+        const uint4* p = reinterpret_cast<const uint4*>(in) + v_lo + tid;
+        long long rem = v_hi - v_lo;   // vectors of this share from the current batch on (uniform)
+        uint4 cur[U], nxt[U];
+        auto fetch = [&](uint4* dst, const uint4* q, long long left) {
+            const int lim = left < (long long)STEP ? (int)(left > 0 ? left : 0) : STEP;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                dst[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (tid + 1024 * u < lim)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(dst[u].x), "=r"(dst[u].y), "=r"(dst[u].z), "=r"(dst[u].w) : "l"(q + 1024 * u));
+            }
+        };
+        fetch(cur, p, rem);
+        int batches = 0;
+#pragma unroll 1
+        while (rem > 0) {
+            fetch(nxt, p + STEP, rem - STEP);
+            if (rem >= STEP) {   // full batch (uniform per CTA): no per-vector bounds
+#pragma unroll
+                for (int u = 0; u < U; ++u) count_vec(cur[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (tid + 1024 * u < (int)rem) count_vec(cur[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+            p += STEP;
+            rem -= STEP;
+            if (++batches == EPOCH_BATCHES && rem > 0) {
+                move_hot_counters();
+                batches = 0;
+            }
+        }
+        done = v_hi * SPV;
+    }
+    // tail, or the whole share when the buffer is not 16-byte aligned: one sample at a time, epochs of 57 344
+    for (long long e0 = done; e0 < s1; e0 += EPOCH_SCALAR) {
+        const long long e1 = (e0 + EPOCH_SCALAR < s1) ? e0 + EPOCH_SCALAR : s1;
+        if (e0 != s0) move_hot_counters();
+        for (long long i = e0 + tid; i < e1; i += 1024) {
             if (FMT == SPX_FMT_CF32) {
-                const float2 v = __ldg(reinterpret_cast<const float2*>(in) + i);
-                count_f(v.x, v.y);
+                count_f(__ldg(reinterpret_cast<const float2*>(in) + i));
             } else {
                 const short2 v = __ldg(reinterpret_cast<const short2*>(in) + i);
-                count_f((float)v.x, (float)v.y);
+                count_f(make_float2((float)v.x, (float)v.y));
             }
         }
-        __syncthreads();
-        for (int w = threadIdx.x; w < words; w += blockDim.x) {
+    }
+    __syncthreads();
+    if (tabs != nullptr) {   // the table as it is (swizzled, packed); tab_stride is a multiple of 4 words
+        uint4* my = reinterpret_cast<uint4*>(tabs + (size_t)blockIdx.x * tab_stride);
+        for (int q = tid; q < quads; q += 1024) my[q] = sh4[q];
+    } else {
+        for (int w = tid; w < words; w += 1024) {
             const unsigned int v = sh[w];
-            const int wo = swz_mask ? (w ^ ((2 * w / bins) & swz_mask)) : w;   // word index before the swizzle (row = 2 w / bins)
+            const int wo = unswizzled(w);
             if (v & 0xffffu) atomicAdd(hist + 2 * wo, v & 0xffffu);
             if (v >> 16) atomicAdd(hist + 2 * wo + 1, v >> 16);
         }
-        __syncthreads();
+    }
+}
+
+// Sum of the CTA-private packed tables into the uint32 histogram: thread (w, q) adds tables q, q + 4, ... for word w
+// (read at its swizzled position), the four partial sums meet in shared memory.  Reads ntabs x 128 KB from L2, plain
+// read-modify-write of `hist` (stream-ordered behind the counting kernel, nothing else touches it).
+__global__ void __launch_bounds__(256) hist_merge_kernel(const unsigned int* __restrict__ tabs, int ntabs, int tab_stride, int words,
+                                                         int bins, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int part[2][4][64];
+    const int wl = threadIdx.x & 63, q = threadIdx.x >> 6, w = blockIdx.x * 64 + wl;
+    const int swz_mask = (bins % 64 == 0) ? 31 : 0;
+    unsigned int lo = 0u, hi = 0u;
+    if (w < words) {
+        const int ws = swz_mask ? (w ^ ((2 * w / bins) & swz_mask)) : w;
+#pragma unroll 8
+        for (int t = q; t < ntabs; t += 4) {
+            const unsigned int v = __ldcg(tabs + (size_t)t * tab_stride + ws);
+            lo += v & 0xffffu;
+            hi += v >> 16;
+        }
+    }
+    part[0][q][wl] = lo;
+    part[1][q][wl] = hi;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int h = threadIdx.x >> 6, bin = 2 * w + h;
+        const unsigned int sum = part[h][0][wl] + part[h][1][wl] + part[h][2][wl] + part[h][3][wl];
+        if (w < words && bin < bins * bins && sum) hist[bin] += sum;
     }
 }
 
@@ -264,6 +393,7 @@ struct TdScratch {
     std::mutex mu;
     DevBuf in, a, b;
     cudaStream_t st = nullptr;
+    cudaMemPool_t pool = nullptr;   // stream-ordered scratch for the private histogram tables (calls on different streams may overlap)
 };
 static TdScratch g_td[64];
 
@@ -315,18 +445,45 @@ extern "C" int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
         const int vec_ok = ((uintptr_t)d_in & 15u) == 0 ? 1 : 0;
         const size_t words = (size_t)((bins * bins + 1) / 2);
-        const size_t smem = ((words + 1) & ~(size_t)1) * sizeof(unsigned int) + (size_t)(bins + 1) * sizeof(double);
-        if (smem <= 200u * 1024u) {
-            // shared-memory privatised counting, one CTA per SM, chunks of <= 65 528 samples (16-bit counters)
-            const int chunk = 65528;
+        const size_t smem = ((words + 3) & ~(size_t)3) * sizeof(unsigned int) + (size_t)(bins + 2) * sizeof(float);
+        if (smem <= 200u * 1024u && in_scale > 0.0 && in_scale < 1e30) {
+            // shared-memory privatised counting: one CTA per SM, each with a contiguous share of the input (a multiple of 8
+            // samples, at least one epoch so that small inputs do not spread over CTAs that each dump a table)
             auto k_c = hist2d_smem_kernel<SPX_FMT_CF32>;
             auto k_i = hist2d_smem_kernel<SPX_FMT_CI16>;
             SPX_CUDA(cudaFuncSetAttribute(k_c, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             SPX_CUDA(cudaFuncSetAttribute(k_i, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            long long blocks = (n + chunk - 1) / chunk;
-            if (blocks > sm) blocks = sm;
-            if (in_fmt == SPX_FMT_CF32) k_c<<<(unsigned)blocks, 1024, smem, st>>>(d_in, n, in_scale, g, d_hist, vec_ok, chunk);
-            else k_i<<<(unsigned)blocks, 1024, smem, st>>>(d_in, n, in_scale, g, d_hist, vec_ok, chunk);
+            long long span = ((n + sm - 1) / sm + 7) & ~7ll;
+            if (span < 32760) span = 32760;
+            const long long blocks = (n + span - 1) / span;
+            HistConst hc;
+            hc.fa = (float)(in_scale * g.inv_step);
+            hc.fb = (float)(-g.start * g.inv_step - 0.5);
+            hc.neg_center = -0.5f * (float)(bins - 1);
+            hc.half_bins = 0.5f * (float)bins;
+            hc.idx_bias = (int)(0x4B400000u * (unsigned)(bins + 1));
+            hc.swz_mask = (bins % 64 == 0) ? 31 : 0;
+            unsigned int* tabs = nullptr;
+            const int tab_stride = (int)((words + 3) & ~(size_t)3);
+            if (blocks > 4) {
+                if (!S->pool) {
+                    cudaMemPoolProps props;
+                    memset(&props, 0, sizeof(props));
+                    props.allocType = cudaMemAllocationTypePinned;
+                    props.location.type = cudaMemLocationTypeDevice;
+                    props.location.id = device;
+                    SPX_CUDA(cudaMemPoolCreate(&S->pool, &props));
+                    unsigned long long keep = ~0ull;   // freed blocks stay in the pool: the next call reuses them
+                    SPX_CUDA(cudaMemPoolSetAttribute(S->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+                }
+                SPX_CUDA(cudaMallocFromPoolAsync((void**)&tabs, (size_t)blocks * tab_stride * sizeof(unsigned int), S->pool, st));
+            }
+            if (in_fmt == SPX_FMT_CF32) k_c<<<(unsigned)blocks, 1024, smem, st>>>(d_in, n, in_scale, g, d_hist, vec_ok, span, tabs, tab_stride, hc);
+            else k_i<<<(unsigned)blocks, 1024, smem, st>>>(d_in, n, in_scale, g, d_hist, vec_ok, span, tabs, tab_stride, hc);
+            if (tabs) {
+                hist_merge_kernel<<<(unsigned)((words + 63) / 64), 256, 0, st>>>(tabs, (int)blocks, tab_stride, (int)words, bins, d_hist);
+                SPX_CUDA(cudaFreeAsync(tabs, st));
+            }
         } else {
             long long blocks = (n + 255) / 256;
             if (blocks > (long long)sm * 8) blocks = (long long)sm * 8;

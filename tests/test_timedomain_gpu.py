@@ -97,3 +97,31 @@ def test_hist2d_packed_counters_do_not_overflow_and_large_tables_fall_back(td):
     got = td.iq_hist2d(off, 2.0, 256)
     nat.device_sync(0)                                                                        # device-memory calls are asynchronous
     assert np.array_equal(got.to_host(), sref.iq_hist2d(y[1:], 2.0, 256))
+
+
+def test_hist2d_hot_counters_across_epochs_and_small_inputs(td):
+    """One table per CTA for its whole share of the input: a CTA that meets the same bin in three or more epochs of
+    32 760 samples must move the counter out before it can wrap (2^24 samples of two values -> ~113 k per CTA), the private
+    tables are merged without atomics, and inputs of <= 4 epochs take the direct flush."""
+    from sdr_iq_visualizer_b200 import _native as nat
+    n = 1 << 24
+    raw = np.empty(2 * n, np.int16)
+    raw[0::2] = 100
+    raw[1::2] = -7
+    raw[2 * 5_000_000: 2 * 5_000_000 + 2 * 70_000: 2] = 101   # a second hot bin inside a few CTAs' shares
+    rng = np.random.default_rng(21)
+    idx = rng.integers(0, n, 50_000)
+    raw[2 * idx] = rng.integers(-2047, 2048, idx.size).astype(np.int16)
+    d = nat.DeviceArray.from_host(raw)
+    h0 = nat.DeviceArray((256, 256), np.uint32, zero=True)
+    got = td.iq_hist2d(d, 2048.0, 256, in_fmt=nat.FMT_CI16, out=h0)
+    got = td.iq_hist2d(d, 2048.0, 256, in_fmt=nat.FMT_CI16, out=got, accumulate=True)        # twice: accumulate on the device
+    nat.device_sync(0)
+    i = raw[0::2].astype(np.float64)
+    q = raw[1::2].astype(np.float64)
+    want = np.histogram2d(i, q, bins=256, range=[[-2048.0, 2048.0]] * 2)[0].astype(np.uint32)
+    assert np.array_equal(got.to_host(), 2 * want)
+    assert int(want.max()) > 16_000_000
+    for m in (1, 7, 32_759, 32_761, 4 * 32_760, 4 * 32_760 + 1, 5 * 32_760 + 3):                 # direct flush <-> merged tables
+        x = sref.synth_iq(m, seed=m).astype(np.complex64)
+        assert np.array_equal(td.iq_hist2d(x, 4.0, 256), sref.iq_hist2d(x, 4.0, 256)), m

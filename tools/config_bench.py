@@ -90,6 +90,20 @@ def c3():
             state["i"] += 1
             td.frame_stats(copies[state["i"] % ncopy], 4096, 4096, in_fmt=fmt, out=outs)
 
+        # device time of 32 back-to-back calls on one stream (CUDA events on that stream), input cold
+        ss = nat.SideStream(0)
+        tm = nat.DeviceTimer(0, ss.handle)
+        per_call = []
+        for rep in range(4):
+            tm.start()
+            for k in range(32):
+                td.iq_hist2d(copies[k % ncopy], r, 256, in_fmt=fmt, out=dh, stream=ss.handle)
+            tm.stop()
+            per_call.append(tm.elapsed_ms() / 32)
+        emit(case=f"C3 I/Q 256x256 histogram, 2^24 {name} samples: device time per call, 32 calls back to back on one stream (memset + count + merge), input cold",
+             kernel_us=round(min(per_call[1:]) * 1e3, 2), GSps=round(L / (min(per_call[1:]) * 1e-3) / 1e9, 1),
+             hbm_frac=round(L * bps / (min(per_call[1:]) * 1e-3) / 1e9 / HBM, 3), bytes_per_sample=bps)
+        ss.sync()
         med, best = timed(cold_hist, warmup=ncopy, iters=3 * ncopy)
         emit(case=f"C3 I/Q 256x256 histogram, 2^24 {name} samples (device-resident, input cold: {ncopy} rotating copies)",
              kernel_us=round(med * 1e3, 2), GSps=round(L / (med * 1e-3) / 1e9, 1),
