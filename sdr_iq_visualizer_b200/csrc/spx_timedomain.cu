@@ -27,6 +27,7 @@ struct HistConst {
     float fa, fb;         // bin estimate u = fa * x + fb = (x * scale - start) / step - 1/2
     float neg_center;     // -(bins - 1) / 2
     float half_bins;      // bins / 2
+    float zone;           // |u - rint(u)| at or above this: within HIST_EPS of an edge, settled exactly (2: never, see hist_constants)
     int idx_bias;         // 0x4B400000 * (bins + 1)
     int swz_mask;         // 31 when every table row starts on a 32-word boundary (bins % 64 == 0), else 0
 };
@@ -146,6 +147,9 @@ __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restric
     const int tid = threadIdx.x;
     const int bins = g.bins, nb2 = bins * bins, words = (nb2 + 1) / 2, quads = (words + 3) / 4;
     uint4* sh4 = reinterpret_cast<uint4*>(sh);
+    // Programmatic dependent launch: the merge kernel behind this one may be scheduled now (it waits for this grid to
+    // complete before it reads); this grid's prologue (zeroed table, thresholds) overlaps the tail of what is in front of it.
+    asm volatile("griddepcontrol.launch_dependents;");
     // The exact decision, in the units of the raw input: thr[i] = the smallest float x whose value v = (double)x * scale
     // reaches numpy's edge i (v >= e_i  <=>  x >= thr[i], the product is monotone in x for scale > 0), thr[bins + 1] = the
     // largest x with v <= stop.  Built once per CTA from the float64 edges; comparing a sample against two neighbouring
@@ -168,12 +172,11 @@ __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restric
     const int swz_mask = hc.swz_mask;
     // Bin estimate u = (v - start)/step - 1/2 as ONE fma in float (constants rounded from float64): its error is below
     // 4e-5 bins for bins <= 320 (|u| <= 160: half an ulp of the product, of the constant and of the result, 1.5e-5 each
-    // at most).  rint(u) through the 1.5 * 2^23 constant: when u is farther than HIST_EPS from a half-integer, i.e.
-    // (v - start)/step is farther than HIST_EPS from an edge, rint(u) IS the bin; otherwise the exact float64 comparison
-    // against numpy's edges decides.  Out-of-range, huge, infinite and NaN estimates give an integer outside [0, bins)
-    // (the bit pattern of u + 1.5 * 2^23 is below or far above the constant's) and are dropped, as numpy does.
+    // at most).  rint(u) through the 1.5 * 2^23 constant: when u is farther than HIST_EPS = 2e-4 from a half-integer, i.e.
+    // (v - start)/step is farther than HIST_EPS from an edge, and inside the range, rint(u) IS the bin; otherwise the
+    // threshold table decides (and drops what is outside [start, stop], infinite or NaN, as numpy does).
     // I and Q go through the four arithmetic steps as one packed pair (FFMA2 / FADD2).
-    constexpr float HIST_EPS = 2e-4f, MAGIC = 12582912.0f;
+    constexpr float MAGIC = 12582912.0f;
     constexpr int MAGIC_BITS = 0x4B400000;
     const float2 fa2 = make_float2(hc.fa, hc.fa), fb2 = make_float2(hc.fb, hc.fb), mg2 = make_float2(MAGIC, MAGIC), nmg2 = make_float2(-MAGIC, -MAGIC),
                  neg2 = make_float2(-1.f, -1.f);
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restric
         b += (x >= thr[b + 1] && b < bins - 1) ? 1 : 0;
         return (x >= thr[0] && x <= thr[bins + 1]) ? b : -1;
     };
+    const float zone = hc.zone;
     auto count_f = [&](float2 f) {
         const float2 u = __ffma2_rn(f, fa2, fb2);
         const float2 m = __fadd2_rn(u, mg2);
@@ -200,10 +204,11 @@ __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restric
         const float2 c = __fadd2_rn(u, nctr2);
         int idx = __float_as_int(m.x) * bins + __float_as_int(m.y) - idx_bias;
         int swz = __float_as_int(m.x) & swz_mask;                              // = bi & swz_mask: the low bits of MAGIC_BITS are 0
-        bool ok = fabsf(c.x) < half_bins && fabsf(c.y) < half_bins;            // two compares, not fmaxf: NaN must fail
-        if (fmaxf(fabsf(d.x), fabsf(d.y)) >= 0.5f - HIST_EPS) {                // near an edge: settle both exactly
+        // the estimate is the answer when both components are clear of every edge and inside the range (two compares for
+        // the range, not fmaxf: a NaN must fail); everything else is settled exactly, or dropped
+        if (!(fabsf(c.x) < half_bins && fabsf(c.y) < half_bins) || fmaxf(fabsf(d.x), fabsf(d.y)) >= zone) {
             const int bi = settle(f.x, __float_as_int(m.x) - MAGIC_BITS), bq = settle(f.y, __float_as_int(m.y) - MAGIC_BITS);
-            ok = (bi | bq) >= 0;
+            if ((bi | bq) < 0) return;
             idx = bi * bins + bq;
             swz = bi & swz_mask;
         }
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restric
         unsigned int val, addr;
         asm volatile("mad.lo.u32 %0, %1, 65535, 1;" : "=r"(val) : "r"((unsigned)idx & 1u));
         asm volatile("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"((unsigned)((idx >> 1) ^ swz)), "r"(sh_base));
-        if (ok) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
     };
     auto count_vec = [&](const uint4& wv) {
         if (FMT == SPX_FMT_CF32) {
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restric
         }
         __syncthreads();
     };
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the input and the zeroed histogram are complete and visible from here
     __syncthreads();
     // this CTA's share of the input: [s0, s1), s0 a multiple of 8 samples
     const long long s0 = (long long)blockIdx.x * span, s1 = (s0 + span < n) ? s0 + span : n;
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(1024) hist2d_smem_kernel(const void* __restric
 __global__ void __launch_bounds__(256) hist_merge_kernel(const unsigned int* __restrict__ tabs, int ntabs, int tab_stride, int words,
                                                          int bins, unsigned int* __restrict__ hist) {
     __shared__ unsigned int part[2][4][64];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched early (programmatic dependent launch): wait for the tables
     const int wl = threadIdx.x & 63, q = threadIdx.x >> 6, w = blockIdx.x * 64 + wl;
     const int swz_mask = (bins % 64 == 0) ? 31 : 0;
     unsigned int lo = 0u, hi = 0u;
@@ -346,6 +353,13 @@ __global__ void __launch_bounds__(256) hist_merge_kernel(const unsigned int* __r
         const unsigned int sum = part[h][0][wl] + part[h][1][wl] + part[h][2][wl] + part[h][3][wl];
         if (w < words && bin < bins * bins && sum) hist[bin] += sum;
     }
+}
+
+// Zeroes the histogram in front of the counting kernel (instead of a memset node, so that the counting kernel can be a
+// programmatic dependent launch and run its prologue next to this).
+__global__ void __launch_bounds__(256) hist_zero_kernel(unsigned int* __restrict__ hist, int n) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) hist[i] = 0u;
 }
 
 template <int FMT>
@@ -387,6 +401,36 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const void* __restrict
             peak_pow[f] = m;
         }
     }
+}
+
+// Constants of the bin estimate.  General case: u = (x * scale - start)/step - 1/2 with an edge zone of HIST_EPS bins.
+// Integer input on a power-of-two grid (ci16, scale = 2^a, step = 2^b, e.g. R = 2048 / 256 bins, or the SigMF scale 2^-15
+// with R = 1): every product, sum and numpy edge is exact, t = (v - start)/step is a multiple of G = min(2^(a-b), 1) and a
+// sixteenth of such samples sits exactly ON an edge.  Shifting the estimate by G/2 makes rint(t - 1/2 + G/2) = floor(t)
+// for every sample, ties included, so the edge zone is switched off; only v = stop (t = bins) and values outside the range
+// fail the range test and take the threshold table.
+static HistConst hist_constants(const HistGrid& g, int in_fmt, double scale) {
+    HistConst hc;
+    const int bins = g.bins;
+    double shift = 0.0;
+    hc.zone = 0.5f - 2e-4f;
+    if (in_fmt == SPX_FMT_CI16) {
+        int ea = 0, eb = 0;
+        const double ma = frexp(scale, &ea), mb = frexp(g.step, &eb);
+        const int k = ea - eb;   // scale / step = 2^k when both mantissas are 1/2
+        const bool exact_edges = g.step * bins == g.stop - g.start && g.start == -g.stop;
+        if (ma == 0.5 && mb == 0.5 && exact_edges && k >= -11 && k <= 6) {
+            shift = k < 0 ? ldexp(1.0, k - 1) : 0.25;
+            hc.zone = 2.0f;
+        }
+    }
+    hc.fa = (float)(scale * g.inv_step);
+    hc.fb = (float)(-g.start * g.inv_step - 0.5 + shift);
+    hc.neg_center = -0.5f * (float)(bins - 1);
+    hc.half_bins = 0.5f * (float)bins;
+    hc.idx_bias = (int)(0x4B400000u * (unsigned)(bins + 1));
+    hc.swz_mask = (bins % 64 == 0) ? 31 : 0;
+    return hc;
 }
 
 struct TdScratch {
@@ -439,7 +483,7 @@ extern "C" int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_
         d_hist = (unsigned int*)S->a.ptr;
         if (accumulate) SPX_CUDA(cudaMemcpyAsync(d_hist, hist, hbytes, cudaMemcpyHostToDevice, st));
     }
-    if (!accumulate) SPX_CUDA(cudaMemsetAsync(d_hist, 0, hbytes, st));
+    bool zeroed = accumulate != 0;
     if (n > 0) {
         int sm = 148;
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
@@ -456,13 +500,7 @@ extern "C" int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_
             long long span = ((n + sm - 1) / sm + 7) & ~7ll;
             if (span < 32760) span = 32760;
             const long long blocks = (n + span - 1) / span;
-            HistConst hc;
-            hc.fa = (float)(in_scale * g.inv_step);
-            hc.fb = (float)(-g.start * g.inv_step - 0.5);
-            hc.neg_center = -0.5f * (float)(bins - 1);
-            hc.half_bins = 0.5f * (float)bins;
-            hc.idx_bias = (int)(0x4B400000u * (unsigned)(bins + 1));
-            hc.swz_mask = (bins % 64 == 0) ? 31 : 0;
+            const HistConst hc = hist_constants(g, in_fmt, in_scale);
             unsigned int* tabs = nullptr;
             const int tab_stride = (int)((words + 3) & ~(size_t)3);
             if (blocks > 4) {
@@ -478,13 +516,34 @@ extern "C" int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_
                 }
                 SPX_CUDA(cudaMallocFromPoolAsync((void**)&tabs, (size_t)blocks * tab_stride * sizeof(unsigned int), S->pool, st));
             }
-            if (in_fmt == SPX_FMT_CF32) k_c<<<(unsigned)blocks, 1024, smem, st>>>(d_in, n, in_scale, g, d_hist, vec_ok, span, tabs, tab_stride, hc);
-            else k_i<<<(unsigned)blocks, 1024, smem, st>>>(d_in, n, in_scale, g, d_hist, vec_ok, span, tabs, tab_stride, hc);
+            cudaLaunchAttribute pdl[1];
+            pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.stream = st;
+            cfg.attrs = pdl;
+            cfg.numAttrs = 1;
+            if (!zeroed) {
+                hist_zero_kernel<<<64, 256, 0, st>>>(d_hist, bins * bins);
+                zeroed = true;
+            }
+            cfg.gridDim = dim3((unsigned)blocks);
+            cfg.blockDim = dim3(1024);
+            cfg.dynamicSmemBytes = smem;
+            SPX_CUDA(cudaLaunchKernelEx(&cfg, in_fmt == SPX_FMT_CF32 ? k_c : k_i, d_in, (long long)n, in_scale, g, d_hist, vec_ok, span, tabs, tab_stride, hc));
             if (tabs) {
-                hist_merge_kernel<<<(unsigned)((words + 63) / 64), 256, 0, st>>>(tabs, (int)blocks, tab_stride, (int)words, bins, d_hist);
+                cfg.gridDim = dim3((unsigned)((words + 63) / 64));
+                cfg.blockDim = dim3(256);
+                cfg.dynamicSmemBytes = 0;
+                SPX_CUDA(cudaLaunchKernelEx(&cfg, hist_merge_kernel, (const unsigned int*)tabs, (int)blocks, tab_stride, (int)words, bins, d_hist));
                 SPX_CUDA(cudaFreeAsync(tabs, st));
             }
         } else {
+            if (!zeroed) {
+                SPX_CUDA(cudaMemsetAsync(d_hist, 0, hbytes, st));
+                zeroed = true;
+            }
             long long blocks = (n + 255) / 256;
             if (blocks > (long long)sm * 8) blocks = (long long)sm * 8;
             if (in_fmt == SPX_FMT_CF32) hist2d_kernel<SPX_FMT_CF32><<<(unsigned)blocks, 256, 0, st>>>(d_in, n, in_scale, g, d_hist, vec_ok);
@@ -492,6 +551,7 @@ extern "C" int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_
         }
         SPX_CUDA(cudaGetLastError());
     }
+    if (!zeroed) SPX_CUDA(cudaMemsetAsync(d_hist, 0, hbytes, st));   // n == 0
     if (mem == SPX_MEM_HOST) {
         SPX_CUDA(cudaMemcpyAsync(hist, d_hist, hbytes, cudaMemcpyDeviceToHost, st));
         SPX_CUDA(cudaStreamSynchronize(st));

@@ -125,3 +125,24 @@ def test_hist2d_hot_counters_across_epochs_and_small_inputs(td):
     for m in (1, 7, 32_759, 32_761, 4 * 32_760, 4 * 32_760 + 1, 5 * 32_760 + 3):                 # direct flush <-> merged tables
         x = sref.synth_iq(m, seed=m).astype(np.complex64)
         assert np.array_equal(td.iq_hist2d(x, 4.0, 256), sref.iq_hist2d(x, 4.0, 256)), m
+
+
+@pytest.mark.parametrize("r,scale,bins", [(2048.0, 1.0, 256), (1.0, 2.0**-15, 256), (32768.0, 1.0, 256), (128.0, 1.0, 256),
+                                          (64.0, 1.0, 256), (2048.0, 1.0, 64), (1000.0, 1.0, 250), (0.5, 2.0**-15, 192)])
+def test_hist2d_ci16_integer_grid(td, r, scale, bins):
+    """int16 input on a power-of-two bin grid (every product and edge exact: samples sit exactly ON edges, the estimate is
+    shifted by half a grid step instead of using an edge zone) next to geometries that are not (1000 / 250, 192 bins):
+    all int16 values, including start, stop (closed right edge), stop + 1 and the extremes."""
+    from sdr_iq_visualizer_b200 import _native as nat
+    rng = np.random.default_rng(int(r * 7) + bins)
+    n = 1 << 18
+    raw = rng.integers(-32768, 32768, 2 * n).astype(np.int16)
+    k = int(round(r / scale))
+    special = np.array([-k, k, -k - 1, k + 1, k - 1, -k + 1, 0, 1, -1, -32768, 32767], np.int64)
+    special = special[(special >= -32768) & (special <= 32767)].astype(np.int16)
+    raw[0:2 * special.size:2] = special
+    raw[1:2 * special.size:2] = special[::-1]
+    got = td.iq_hist2d(raw, r, bins, in_fmt=nat.FMT_CI16, in_scale=scale)
+    want = sref.iq_hist2d(sref.unpack_ci16(raw, scale), r, bins)
+    np.testing.assert_array_equal(got, want)
+    assert got.sum() > 0

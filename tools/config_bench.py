@@ -100,7 +100,7 @@ def c3():
                 td.iq_hist2d(copies[k % ncopy], r, 256, in_fmt=fmt, out=dh, stream=ss.handle)
             tm.stop()
             per_call.append(tm.elapsed_ms() / 32)
-        emit(case=f"C3 I/Q 256x256 histogram, 2^24 {name} samples: device time per call, 32 calls back to back on one stream (memset + count + merge), input cold",
+        emit(case=f"C3 I/Q 256x256 histogram, 2^24 {name} samples: device time per call, 32 calls back to back on one stream (zero + count + merge), input cold",
              kernel_us=round(min(per_call[1:]) * 1e3, 2), GSps=round(L / (min(per_call[1:]) * 1e-3) / 1e9, 1),
              hbm_frac=round(L * bps / (min(per_call[1:]) * 1e-3) / 1e9 / HBM, 3), bytes_per_sample=bps)
         ss.sync()
