@@ -374,14 +374,15 @@ def main():
     SLOT = 1 << 22
     n_full, tail = divmod(L_STEP, SLOT)
     slot_sizes = [SLOT] * n_full + ([tail] if tail else [])
-    rg = ringmod.StreamRing(pl, n_slots=4, slot_samples=SLOT, wf_rows=True, welch=True, maxhold=True, vmin=VMIN, vmax=VMAX,
+    RING_SLOTS = 6      # five in flight + the one the producer fills: with fewer the two upload streams cannot both stay busy
+    rg = ringmod.StreamRing(pl, n_slots=RING_SLOTS, slot_samples=SLOT, wf_rows=True, welch=True, maxhold=True, vmin=VMIN, vmax=VMAX,
                             features=True, sample_rate=FS)
     e2e_steps = max(3, min(args.steps, 10))
 
     ring_state = {"pending": 0, "last": None}
 
     def ring_pass(fill, drain):
-        """One step = one second of the stream through the ring (slots are collected two commits behind).  The stream is
+        """One step = one second of the stream through the ring (slots are collected RING_SLOTS - 1 commits behind).  The stream is
         continuous: consecutive steps keep the pipeline full, only the end of the timed region drains it."""
         pos = 0
         for n in slot_sizes:
@@ -391,7 +392,7 @@ def main():
             rg.commit(n)
             pos += n
             ring_state["pending"] += 1
-            if ring_state["pending"] >= 3:
+            if ring_state["pending"] >= RING_SLOTS - 1:
                 ring_state["last"] = rg.collect(); rg.release(); ring_state["pending"] -= 1
         while drain and ring_state["pending"]:
             ring_state["last"] = rg.collect(); rg.release(); ring_state["pending"] -= 1
@@ -550,7 +551,7 @@ def main():
            "h2d_bytes_per_step": int(ring_h2d), "d2h_bytes_per_step": int(ring_d2h), "steps": e2e_steps,
            "ms_per_step": round(dt_ring / e2e_steps * 1e3, 3),
            "h2d_gbs_per_gpu": round(ring_h2d * e2e_steps / dt_ring / 1e9, 2), "d2h_gbs_per_gpu": round(ring_d2h * e2e_steps / dt_ring / 1e9, 2),
-           "path": "spx_ring_* (pinned ring, 4 slots x 2^22 samples): per slot H2D -> fused STFT + Welch finalize + classifier "
+           "path": "spx_ring_* (pinned ring, 6 slots x 2^22 samples, uploads on two alternating streams): per slot H2D -> fused STFT + Welch finalize + classifier "
                    "features -> D2H of rows / Welch / max-hold / PSD / features; in-place producer (slots are the DMA target)",
            "memcpy_producer_first_pass_ms": round(dt_fill * 1e3, 1),
            "one_shot_call": {"value": round(world * L_STEP * call_steps / dt_call / 1e6, 1), "ms_per_step": round(dt_call / call_steps * 1e3, 3),

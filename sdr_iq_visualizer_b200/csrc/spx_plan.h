@@ -26,6 +26,10 @@ struct spx_plan {
     std::vector<double> win64;
     double sum_w2 = 0.0, sum_w = 0.0;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // the ingest ring uploads consecutive slots on alternating streams (s_h2d, s_h2d_alt): two uploads in flight keep the H2D
+    // direction full while the D2H direction is busy -- a single copy at a time leaves ~35 us per 16 MB slot on the table
+    // (tools/micro/copy_gap.cu: 386 vs 355 us per slot; needs >= 5 slots in flight in the ring to show, profiles/r02_e2e_ring_depth.jsonl)
+    cudaStream_t s_h2d_alt = nullptr;
     std::vector<cudaEvent_t> events;
     size_t piece_bytes = 16u << 20;  // H2D piece size of the host pipeline
     size_t peer_piece_bytes = 48u << 20;  // uint8 rows per piece of the peer-output pipeline (two staging buffers)

@@ -9,6 +9,9 @@
 // carried device-to-device into the head of the next slot's device buffer, never re-sent over PCIe.
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <mutex>
 #include <new>
 #include <vector>
@@ -26,12 +29,25 @@ struct RingSlot {
     float *d_max = nullptr, *h_max = nullptr;
     double *d_pdb = nullptr, *h_pdb = nullptr;       // Welch PSD of the slot in dB (want_features)
     spx_features *d_feat = nullptr, *h_feat = nullptr;
-    cudaEvent_t e_h2d = nullptr, e_kernel = nullptr, e_done = nullptr;
+    // Welch sum, PSD in dB, max-hold and the feature record live in ONE device block and ONE pinned block ([welch][pdb][max][feat]):
+    // a slot's small results leave in a single copy -- as four copies they held the D2H queue ~40 us per 350 us slot
+    char *d_small = nullptr, *h_small = nullptr;
+    size_t small_bytes = 0;
+    cudaEvent_t e_h2d = nullptr, e_stft = nullptr, e_kernel = nullptr, e_done = nullptr;
+    cudaEvent_t t_h2d0 = nullptr, t_d2h0 = nullptr;   // SPX_RING_TRACE=1 only: start of the H2D / of the rows' D2H
     long long seq = -1, n_frames = 0, first_frame = 0, h2d_bytes = 0, d2h_bytes = 0;
     bool has_features = false;
     int state = 0;                   // 0 free, 1 acquired (being filled), 2 committed (in flight / ready)
 };
 
+}  // namespace spx
+
+namespace spx {
+// the (nfft - hop)-sample tail of a slot, copied to the head of the next slot's device buffer (sample sizes are multiples of 4 bytes)
+__global__ void __launch_bounds__(256) ring_carry_kernel(unsigned int* __restrict__ dst, const unsigned int* __restrict__ src, unsigned n_words) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n_words) dst[i] = src[i];
+}
 }  // namespace spx
 
 struct spx_ring {
@@ -46,6 +62,8 @@ struct spx_ring {
     long long seq = 0;
     long long carry = 0;             // samples already on the device that the next frames start in
     long long frames_total = 0, samples_total = 0, h2d_total = 0, d2h_total = 0;
+    bool trace = false;              // SPX_RING_TRACE=1: timed events, one timeline line per released slot on stderr
+    cudaEvent_t e_ref = nullptr;
     std::mutex mu;
 };
 
@@ -59,18 +77,16 @@ static void ring_free(spx_ring* r) {
         if (s.h_wf) cudaFreeHost(s.h_wf);
         if (s.d_db) cudaFree(s.d_db);
         if (s.h_db) cudaFreeHost(s.h_db);
-        if (s.d_welch) cudaFree(s.d_welch);
-        if (s.h_welch) cudaFreeHost(s.h_welch);
-        if (s.d_max) cudaFree(s.d_max);
-        if (s.h_max) cudaFreeHost(s.h_max);
-        if (s.d_pdb) cudaFree(s.d_pdb);
-        if (s.h_pdb) cudaFreeHost(s.h_pdb);
-        if (s.d_feat) cudaFree(s.d_feat);
-        if (s.h_feat) cudaFreeHost(s.h_feat);
+        if (s.d_small) cudaFree(s.d_small);
+        if (s.h_small) cudaFreeHost(s.h_small);
         if (s.e_h2d) cudaEventDestroy(s.e_h2d);
+        if (s.e_stft) cudaEventDestroy(s.e_stft);
+        if (s.t_h2d0) cudaEventDestroy(s.t_h2d0);
+        if (s.t_d2h0) cudaEventDestroy(s.t_d2h0);
         if (s.e_kernel) cudaEventDestroy(s.e_kernel);
         if (s.e_done) cudaEventDestroy(s.e_done);
     }
+    if (r->e_ref) cudaEventDestroy(r->e_ref);
     delete r;
 }
 
@@ -93,6 +109,12 @@ extern "C" int spx_ring_create(spx_ring** out, spx_plan* plan, const spx_ring_co
     r->frames_max = (cfg->slot_samples + (long long)N) / plan->cfg.hop + 1;
     r->slots.resize((size_t)cfg->n_slots);
     cudaError_t e = cudaSuccess;
+    const char* tr = getenv("SPX_RING_TRACE");
+    r->trace = tr != nullptr && tr[0] == '1';
+    if (r->trace) {
+        cudaEventCreate(&r->e_ref);
+        cudaEventRecord(r->e_ref, plan->s_h2d);
+    }
     for (RingSlot& s : r->slots) {
         const size_t rows = (size_t)r->frames_max * N;
         if ((e = cudaHostAlloc(&s.h_in, (size_t)cfg->slot_samples * r->elt, cudaHostAllocPortable)) != cudaSuccess) break;
@@ -105,24 +127,35 @@ extern "C" int spx_ring_create(spx_ring** out, spx_plan* plan, const spx_ring_co
             if ((e = cudaMalloc((void**)&s.d_db, rows * sizeof(float))) != cudaSuccess) break;
             if ((e = cudaHostAlloc((void**)&s.h_db, rows * sizeof(float), cudaHostAllocPortable)) != cudaSuccess) break;
         }
-        if (cfg->want_welch) {
-            if ((e = cudaMalloc((void**)&s.d_welch, N * sizeof(double))) != cudaSuccess) break;
-            if ((e = cudaHostAlloc((void**)&s.h_welch, N * sizeof(double), cudaHostAllocPortable)) != cudaSuccess) break;
+        {
+            size_t off = 0, o_welch = 0, o_pdb = 0, o_max = 0, o_feat = 0;
+            if (cfg->want_welch) { o_welch = off; off += N * sizeof(double); }
+            if (cfg->want_features) { o_pdb = off; off += N * sizeof(double); }
+            if (cfg->want_maxhold) { o_max = off; off += N * sizeof(float); }
+            off = (off + 7) & ~(size_t)7;
+            if (cfg->want_features) { o_feat = off; off += sizeof(spx_features); }
+            s.small_bytes = off;
+            if (off) {
+                if ((e = cudaMalloc((void**)&s.d_small, off)) != cudaSuccess) break;
+                if ((e = cudaHostAlloc((void**)&s.h_small, off, cudaHostAllocPortable)) != cudaSuccess) break;
+                memset(s.h_small, 0, off);
+                if (cfg->want_welch) { s.d_welch = (double*)(s.d_small + o_welch); s.h_welch = (double*)(s.h_small + o_welch); }
+                if (cfg->want_maxhold) { s.d_max = (float*)(s.d_small + o_max); s.h_max = (float*)(s.h_small + o_max); }
+                if (cfg->want_features) {
+                    s.d_pdb = (double*)(s.d_small + o_pdb); s.h_pdb = (double*)(s.h_small + o_pdb);
+                    s.d_feat = (spx_features*)(s.d_small + o_feat); s.h_feat = (spx_features*)(s.h_small + o_feat);
+                }
+            }
         }
-        if (cfg->want_maxhold) {
-            if ((e = cudaMalloc((void**)&s.d_max, N * sizeof(float))) != cudaSuccess) break;
-            if ((e = cudaHostAlloc((void**)&s.h_max, N * sizeof(float), cudaHostAllocPortable)) != cudaSuccess) break;
+        const unsigned evf = r->trace ? cudaEventDefault : cudaEventDisableTiming;
+        if ((e = cudaEventCreateWithFlags(&s.e_h2d, evf)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.e_stft, evf)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.e_kernel, evf)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&s.e_done, evf)) != cudaSuccess) break;
+        if (r->trace) {
+            if ((e = cudaEventCreate(&s.t_h2d0)) != cudaSuccess) break;
+            if ((e = cudaEventCreate(&s.t_d2h0)) != cudaSuccess) break;
         }
-        if (cfg->want_features) {
-            if ((e = cudaMalloc((void**)&s.d_pdb, N * sizeof(double))) != cudaSuccess) break;
-            if ((e = cudaHostAlloc((void**)&s.h_pdb, N * sizeof(double), cudaHostAllocPortable)) != cudaSuccess) break;
-            if ((e = cudaMalloc((void**)&s.d_feat, sizeof(spx_features))) != cudaSuccess) break;
-            if ((e = cudaHostAlloc((void**)&s.h_feat, sizeof(spx_features), cudaHostAllocPortable)) != cudaSuccess) break;
-            memset(s.h_feat, 0, sizeof(spx_features));
-        }
-        if ((e = cudaEventCreateWithFlags(&s.e_h2d, cudaEventDisableTiming)) != cudaSuccess) break;
-        if ((e = cudaEventCreateWithFlags(&s.e_kernel, cudaEventDisableTiming)) != cudaSuccess) break;
-        if ((e = cudaEventCreateWithFlags(&s.e_done, cudaEventDisableTiming)) != cudaSuccess) break;
     }
     if (e != cudaSuccess) {
         ring_free(r);
@@ -136,6 +169,7 @@ extern "C" int spx_ring_destroy(spx_ring* r) {
     if (!r) return SPX_OK;
     cudaSetDevice(r->plan->cfg.device);
     cudaStreamSynchronize(r->plan->s_h2d);
+    cudaStreamSynchronize(r->plan->s_h2d_alt);
     cudaStreamSynchronize(r->plan->s_compute);
     cudaStreamSynchronize(r->plan->s_d2h);
     ring_free(r);
@@ -167,14 +201,17 @@ extern "C" int spx_ring_commit(spx_ring* r, int64_t n_samples) {
     const long long carry = r->carry;
     NvtxRange r_commit("spx ring commit: H2D -> STFT -> D2H");
     // H2D of the new samples behind the carried tail
-    if (n_samples) SPX_CUDA(cudaMemcpyAsync(s.d_in + (size_t)carry * elt, s.h_in, (size_t)n_samples * elt, cudaMemcpyHostToDevice, pl->s_h2d));
-    SPX_CUDA(cudaEventRecord(s.e_h2d, pl->s_h2d));
+    cudaStream_t s_up = (r->seq & 1) ? pl->s_h2d_alt : pl->s_h2d;   // consecutive slots upload on alternating streams (spx_plan.h)
+    if (r->trace) SPX_CUDA(cudaEventRecord(s.t_h2d0, s_up));
+    if (n_samples) SPX_CUDA(cudaMemcpyAsync(s.d_in + (size_t)carry * elt, s.h_in, (size_t)n_samples * elt, cudaMemcpyHostToDevice, s_up));
+    SPX_CUDA(cudaEventRecord(s.e_h2d, s_up));
     SPX_CUDA(cudaStreamWaitEvent(pl->s_compute, s.e_h2d, 0));
     const long long avail = carry + n_samples;
     const long long F = spx_frame_count(avail, N, hop);
     if (s.d_welch) SPX_CUDA(cudaMemsetAsync(s.d_welch, 0, (size_t)N * sizeof(double), pl->s_compute));
     if (s.d_max) SPX_CUDA(cudaMemsetAsync(s.d_max, 0, (size_t)N * sizeof(float), pl->s_compute));
     SPX_TRY(stft_launch_device(pl, s.d_in, 1, 0, F, s.d_db, s.d_wf, nullptr, s.d_welch, s.d_max, r->cfg.vmin, r->cfg.vmax, pl->s_compute));
+    SPX_CUDA(cudaEventRecord(s.e_stft, pl->s_compute));   // the rows are complete here: their copy does not wait for the measurements
     // classifier measurements of this slot's Welch block, right behind the STFT kernel on the same stream
     const bool feats = s.d_feat != nullptr && F > 0;
     if (feats) {
@@ -186,20 +223,24 @@ extern "C" int spx_ring_commit(spx_ring* r, int64_t n_samples) {
     const long long consumed = F * hop;
     const long long new_carry = avail - consumed;
     RingSlot& nx = r->slots[(size_t)((r->head + 1) % r->cfg.n_slots)];
-    if (new_carry > 0)
-        SPX_CUDA(cudaMemcpyAsync(nx.d_in, s.d_in + (size_t)consumed * elt, (size_t)new_carry * elt, cudaMemcpyDeviceToDevice, pl->s_compute));
+    if (new_carry > 0) {
+        // a kernel, not cudaMemcpyAsync: a device-to-device copy would go to a copy engine and sit between the H2D / D2H transfers
+        const unsigned n_words = (unsigned)((size_t)new_carry * elt / 4);
+        ring_carry_kernel<<<(n_words + 255) / 256, 256, 0, pl->s_compute>>>(reinterpret_cast<unsigned int*>(nx.d_in),
+                                                                             reinterpret_cast<const unsigned int*>(s.d_in + (size_t)consumed * elt), n_words);
+        SPX_CUDA(cudaGetLastError());
+    }
     SPX_CUDA(cudaEventRecord(s.e_kernel, pl->s_compute));
-    // drain the slot's results
-    SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, s.e_kernel, 0));
+    // drain the slot's results: the rows as soon as the STFT kernel is done, the small block (one copy) behind the measurements
     long long d2h = 0;
+    SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, s.e_stft, 0));
+    if (r->trace) SPX_CUDA(cudaEventRecord(s.t_d2h0, pl->s_d2h));
     if (s.d_wf && F) { SPX_CUDA(cudaMemcpyAsync(s.h_wf, s.d_wf, (size_t)F * N, cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += F * N; }
     if (s.d_db && F) { SPX_CUDA(cudaMemcpyAsync(s.h_db, s.d_db, (size_t)F * N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += F * N * 4; }
-    if (s.d_welch) { SPX_CUDA(cudaMemcpyAsync(s.h_welch, s.d_welch, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += N * 8; }
-    if (s.d_max) { SPX_CUDA(cudaMemcpyAsync(s.h_max, s.d_max, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, pl->s_d2h)); d2h += N * 4; }
-    if (feats) {
-        SPX_CUDA(cudaMemcpyAsync(s.h_pdb, s.d_pdb, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, pl->s_d2h));
-        SPX_CUDA(cudaMemcpyAsync(s.h_feat, s.d_feat, sizeof(spx_features), cudaMemcpyDeviceToHost, pl->s_d2h));
-        d2h += N * 8 + (long long)sizeof(spx_features);
+    SPX_CUDA(cudaStreamWaitEvent(pl->s_d2h, s.e_kernel, 0));
+    if (s.small_bytes) {
+        SPX_CUDA(cudaMemcpyAsync(s.h_small, s.d_small, s.small_bytes, cudaMemcpyDeviceToHost, pl->s_d2h));
+        d2h += (long long)s.small_bytes;
     }
     s.has_features = feats;
     SPX_CUDA(cudaEventRecord(s.e_done, pl->s_d2h));
@@ -250,6 +291,13 @@ extern "C" int spx_ring_release(spx_ring* r) {
     if (r->in_flight == 0) return spx_set_error(SPX_E_BUSY, "nothing to release");
     RingSlot& s = r->slots[(size_t)r->tail];
     SPX_CUDA(cudaEventSynchronize(s.e_done));
+    if (r->trace) {
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        cudaEvent_t ev[6] = {s.t_h2d0, s.e_h2d, s.e_stft, s.e_kernel, s.t_d2h0, s.e_done};
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], r->e_ref, ev[i]);
+        fprintf(stderr, "spx_ring_trace seq %lld us: h2d %.0f..%.0f stft_done %.0f meas_done %.0f d2h %.0f..%.0f\n", s.seq, t[0] * 1e3,
+                t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+    }
     s.state = 0;
     r->tail = (r->tail + 1) % r->cfg.n_slots;
     r->in_flight--;
