@@ -10,6 +10,10 @@ per-buffer dicts (/root/reference/app/sdr/streamer.py:18,186-200).
 
 Frames are continuous across slots; every slot is one Welch / max-hold block.  H2D / D2H byte counters
 are reported separately in ``stats()``.
+
+Ring depth: consecutive slots upload on two alternating streams.  A producer that keeps ``n_slots - 1`` commits in flight
+reaches the PCIe copy ceiling with ``n_slots >= 6`` (0.94 - 1.00 of it on config 2); with 4 slots only one upload is in
+flight at a time and ~10 % is lost (profiles/r02_e2e_ring_depth.jsonl).
 """
 from __future__ import annotations
 
