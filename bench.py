@@ -71,6 +71,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.sm, self.mask, self.max_mhz, self.power = [], 0, None, []
+        self.pcie = []            # (link generation, width) seen while sampling: a downtrained link explains a low copy ceiling
+        self.pcie_max = None
         self._stop = threading.Event()
         self._thr = None
         self._nvml = None
@@ -88,6 +90,10 @@ class ClockSampler:
                     phys = self.idx
             h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.pcie_max = (int(pynvml.nvmlDeviceGetMaxPcieLinkGeneration(h)), int(pynvml.nvmlDeviceGetMaxPcieLinkWidth(h)))
+            except Exception:
+                self.pcie_max = None
             self._nvml = (pynvml, h)
         except Exception:
             self._nvml = None
@@ -112,6 +118,8 @@ class ClockSampler:
                     self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                     self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
                     self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    if len(self.sm) % 8 == 1:
+                        self.pcie.append((int(nv.nvmlDeviceGetCurrPcieLinkGeneration(h)), int(nv.nvmlDeviceGetCurrPcieLinkWidth(h))))
                 else:
                     self._sample_smi()
             except Exception:
@@ -126,7 +134,10 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": reasons, "samples": len(self.sm), "source": "nvml" if self._nvml else "nvidia-smi",
                 "power_w_max": round(max(self.power), 1) if self.power else None,
-                "sm_mhz_min": float(min(self.sm)) if self.sm else None}
+                "sm_mhz_min": float(min(self.sm)) if self.sm else None,
+                "pcie_link": None if not self.pcie else {"gen_min": min(g for g, _ in self.pcie), "width_min": min(w for _, w in self.pcie),
+                                                         "gen_max": self.pcie_max[0] if self.pcie_max else None,
+                                                         "width_max": self.pcie_max[1] if self.pcie_max else None}}
 
 
 def dist_setup(n_gpus):
