@@ -39,6 +39,7 @@ struct Big2Params {
     int lanes;
     int lag, slots;          // slots = 2 lag + 2
     int rotate;              // duty rotation among the warps (env SPX_BIG2_ROTATE, default 1)
+    int l2_prefetch;         // request the next frame's column tile into L2 one role early (on for hop >= N; env SPX_BIG2_L2PF)
 };
 
 // shared memory: [staging tile 32 KB, 1024-aligned][warp-local exchange buffer][window of this column tile, [16 a][256 tid]]
@@ -62,6 +63,10 @@ __device__ __forceinline__ void tma_load_tile(unsigned dst, const CUtensorMap* t
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar)
                  : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_tile_l2(const CUtensorMap* tmap, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y) : "memory");
 }
 
 // The role sequence of a CTA with lag D: iteration i runs A(i) (if i < n) and then B(i - D) (if 0 <= i - D < n).
@@ -154,6 +159,9 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
         // the next role is the B role of the very frame this A role produces (a lane with a single frame): its tile can only
         // be requested after this role's release
         const bool hold = has_next && kind == 0 && nx.ph == 1 && nx.s(lag) == s;
+        // the column tile of this lane's next frame comes from HBM and is only requested one role from now: ask L2 for it now
+        if (p.l2_prefetch && tid == 0 && kind == 0 && s + 1 < n_l)
+            tma_prefetch_tile_l2(&tm_in, 32 * g, p.in_row0 + (lane + (s + 1) * p.lanes) * p.hop_rows);
         mbar_wait(full_u32, parity & 1u);
         parity += 1u;
         big2_load_tile(v, tid, stage, kind == 0 ? wf_ptr : nullptr);
@@ -300,6 +308,10 @@ int big2_launch_stream(spx_plan* pl, const void* in, long long frames, long long
     p.lag = lag;
     p.rotate = 1;
     if (const char* e = getenv("SPX_BIG2_ROTATE")) p.rotate = atoi(e);
+    // measured (profiles/r02_k2v2_l2_prefetch_ab.txt): + 2 % without overlap (hop = N: the whole tile comes from HBM), - 1 % at 50 %
+    // overlap (half of the tile is an L2 hit already)
+    p.l2_prefetch = p.hop_rows >= 256 ? 1 : 0;
+    if (const char* e = getenv("SPX_BIG2_L2PF")) p.l2_prefetch = atoi(e);
     p.slots = slots;
     SPX_CUDA(cudaMemsetAsync(p.done, 0, (size_t)lanes * slots * sizeof(int), st));
 

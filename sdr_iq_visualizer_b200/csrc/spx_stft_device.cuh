@@ -35,6 +35,7 @@ struct StftParams {
     int frames_per_chunk;        // accumulator flush granularity (<= 256)
     int chunks_per_stream;
     long long total_chunks;
+    int l2_prefetch;             // K1v2: frames ahead whose new samples are requested into L2 (0 = off; set by the launcher when hop >= N)
 };
 
 // ------------------------------------------------------------------ device/host primitives
