@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) hist2d_kernel(const void* __restrict__ in
 }
 
 // Shared-memory privatised variant (north_star: "a shared-memory I/Q 2-D histogram for the constellation view"), used
-// when bins^2 16-bit counters fit in shared memory (bins <= 320; 128 KB for 256 x 256).  Real constellations pile up
+// when bins^2 16-bit counters fit in 200 KB of shared memory (bins <= 318; 128 KB for 256 x 256).  Real constellations pile up
 // on a few thousand bins, and RED.ADD on the same L2 sectors from every SM serialises (ncu: 261 us for 2^24 samples with
 // the global-atomic kernel above, DRAM at 6 %).  Here every CTA keeps ONE table of packed 16-bit counters in shared memory
 // for its whole share of the input (two per word, ATOMS.ADD of 1 or 1<<16):
@@ -519,8 +519,7 @@ extern "C" int spx_iq_hist2d(int32_t device, int32_t mem, const void* in, int32_
             cudaLaunchAttribute pdl[1];
             pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             pdl[0].val.programmaticStreamSerializationAllowed = 1;
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
+            cudaLaunchConfig_t cfg = {};
             cfg.stream = st;
             cfg.attrs = pdl;
             cfg.numAttrs = 1;
