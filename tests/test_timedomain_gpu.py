@@ -146,3 +146,13 @@ def test_hist2d_ci16_integer_grid(td, r, scale, bins):
     want = sref.iq_hist2d(sref.unpack_ci16(raw, scale), r, bins)
     np.testing.assert_array_equal(got, want)
     assert got.sum() > 0
+
+
+def test_hist2d_fuzz_against_numpy():
+    """Randomised bins / range / scale / length / format with planted edge values, NaN, infinities and extremes
+    (tools/fuzz_hist2d.py): every count equal to np.histogram2d."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_hist2d.py"), "120", "7"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 mismatches" in r.stdout
