@@ -84,7 +84,7 @@ struct Big2Seq {
     __device__ __forceinline__ int s(int lag) const { return ph == 0 ? it : it - lag; }
 };
 
-template <bool ACC>
+template <bool ACC, int FMT>
 __global__ void __launch_bounds__(256, 2)
 big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_t) {
     extern __shared__ unsigned char smem_raw_b2[];
@@ -121,10 +121,11 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
     const float* wf_ptr = p.wtab != nullptr ? wfull + tid : nullptr;
 
     auto issue = [&](int kind, int s) {     // elected thread: start the TMA load of that role's tile
-        mbar_expect_tx(full_u32, BIG2_STAGE);
-        if (kind == 0) {
-            tma_load_tile(stage_u32, &tm_in, 32 * g, p.in_row0 + (lane + s * p.lanes) * p.hop_rows, full_u32);
+        if (kind == 0) {   // cf32: box {128 B, 256 rows}; ci16: box {64 B, 256 rows} (x in 4-byte units)
+            mbar_expect_tx(full_u32, FMT == FMT_CF32 ? BIG2_STAGE : BIG2_STAGE / 2);
+            tma_load_tile(stage_u32, &tm_in, (FMT == FMT_CF32 ? 32 : 16) * g, p.in_row0 + (lane + s * p.lanes) * p.hop_rows, full_u32);
         } else {
+            mbar_expect_tx(full_u32, BIG2_STAGE);
             const int slot = s % slots;
             const int target = 16 * (s / slots + 1);       // the 16 CTAs of the lane release once per visit of the slot
             // the tile is read by the TMA unit straight from L2 (the point of coherence), never through this SM's L1: a
@@ -161,10 +162,11 @@ big2_kernel(const Big2Params p, const __grid_constant__ CUtensorMap tm_in, const
         const bool hold = has_next && kind == 0 && nx.ph == 1 && nx.s(lag) == s;
         // the column tile of this lane's next frame comes from HBM and is only requested one role from now: ask L2 for it now
         if (p.l2_prefetch && tid == 0 && kind == 0 && s + 1 < n_l)
-            tma_prefetch_tile_l2(&tm_in, 32 * g, p.in_row0 + (lane + (s + 1) * p.lanes) * p.hop_rows);
+            tma_prefetch_tile_l2(&tm_in, (FMT == FMT_CF32 ? 32 : 16) * g, p.in_row0 + (lane + (s + 1) * p.lanes) * p.hop_rows);
         mbar_wait(full_u32, parity & 1u);
         parity += 1u;
-        big2_load_tile(v, tid, stage, kind == 0 ? wf_ptr : nullptr);
+        if (FMT == FMT_CI16 && kind == 0) big2_load_tile_ci16(v, tid, stage, wf_ptr);
+        else big2_load_tile(v, tid, stage, kind == 0 ? wf_ptr : nullptr);
         // The only block barrier of the role, placed where the warps are still aligned (they all woke on the same TMA
         // completion): the staged tile is consumed (every value went through a butterfly above), the previous role's scratch
         // stores are issued and its uint8 tile is complete.  The exchange through X below is warp-local (__syncwarp).
@@ -246,10 +248,10 @@ int big2_plan_init(spx_plan* pl) {
     return SPX_OK;
 }
 
-// K2v2 handles: cf32 input, N = 65536, hop a multiple of 256 samples, 16-byte aligned stream start, outputs among
+// K2v2 handles: cf32 or ci16 input, N = 65536, hop a multiple of 256 samples, 16-byte aligned stream start, outputs among
 // {uint8 rows, Welch sum, max-hold}.  Everything else goes through the two-kernel path of spx_bigfft.cu.
 bool big2_eligible(const spx_plan* pl, const void* in, const float* db_rows, const float2* spec_rows) {
-    if (pl->cfg.nfft != BIG2_N || pl->cfg.in_fmt != SPX_FMT_CF32 || pl->d_big2 == nullptr) return false;
+    if (pl->cfg.nfft != BIG2_N || pl->d_big2 == nullptr) return false;
     if (pl->cfg.variant == 1) return false;                    // variant 1 = the round-1 two-kernel path, kept for comparison
     if (db_rows != nullptr || spec_rows != nullptr) return false;
     if (pl->cfg.hop % 256 != 0 || ((uintptr_t)in & 15u) != 0) return false;
@@ -260,9 +262,11 @@ int big2_launch_stream(spx_plan* pl, const void* in, long long frames, long long
                        float* maxhold, float vmin, float vmax, cudaStream_t st, int sys_atomics) {
     if (frames <= 0) return SPX_OK;
     const bool acc = welch_acc != nullptr || maxhold != nullptr;
-    auto k_acc = big2_kernel<true>;
-    auto k_rows = big2_kernel<false>;
-    static int occ_cache[64] = {0};
+    const bool ci16 = pl->cfg.in_fmt == SPX_FMT_CI16;
+    auto k_acc = ci16 ? big2_kernel<true, FMT_CI16> : big2_kernel<true, FMT_CF32>;
+    auto k_rows = ci16 ? big2_kernel<false, FMT_CI16> : big2_kernel<false, FMT_CF32>;
+    static int occ_cache2[2][64] = {{0}};
+    int* occ_cache = occ_cache2[ci16 ? 1 : 0];
     int dev = 0;
     SPX_CUDA(cudaGetDevice(&dev));
     if (occ_cache[dev & 63] == 0) {
@@ -320,9 +324,18 @@ int big2_launch_stream(spx_plan* pl, const void* in, long long frames, long long
     const cuuint32_t box[2] = {32, 256}, estr[2] = {1, 1};
     const cuuint64_t gdim_in[2] = {512, (cuuint64_t)(((frames - 1) * (long long)pl->cfg.hop + BIG2_N) / 256)};
     const cuuint64_t gdim_t[2] = {512, (cuuint64_t)(lanes * slots * 256)};
-    CUresult r = tmap_encoder()(&tm_in, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(in), gdim_in, gstride, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (ci16) {   // rows of 256 samples = 1 KB, column tile = 16 samples = 64 B
+        const cuuint64_t gstride_i[1] = {1024}, gdim_i[2] = {256, gdim_in[1]};
+        const cuuint32_t box_i[2] = {16, 256};
+        r = tmap_encoder()(&tm_in, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(in), gdim_i, gstride_i, box_i, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        r = tmap_encoder()(&tm_in, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(in), gdim_in, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r == CUDA_SUCCESS)
         r = tmap_encoder()(&tm_t, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, p.scratch, gdim_t, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

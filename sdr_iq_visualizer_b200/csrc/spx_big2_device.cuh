@@ -43,6 +43,27 @@ SPX_HD void big2_load_tile(float2* v, int tid, const void* stage, const float* w
     }
     dft16_layer1(v);
 }
+// The same for int16 input (role A only): the TMA box is {64 B x 256 rows} with CU_TENSOR_MAP_SWIZZLE_64B (the 16-byte chunk
+// index inside a 64-byte row is XORed with bits 7..8 of the address, i.e. with (row >> 1) & 3): the 8 rows a half-warp
+// touches fall on 8 distinct (128-byte half, chunk) positions, 2-way conflicts between its two halves as in K1v2.
+SPX_HD unsigned swz64(unsigned byte) { return byte ^ ((byte >> 3) & 0x30u); }
+template <int WS = 256>
+SPX_HD void big2_load_tile_ci16(float2* v, int tid, const void* stage, const float* w) {
+    const int b = k2_b_of(tid), c = k2_c_of(tid);
+    const unsigned off0 = swz64(4u * (unsigned)(16 * b + c));   // 64 (16 a + b) + 4 c: a only moves bits >= 10
+    const char* st = reinterpret_cast<const char*>(stage);
+#pragma unroll
+    for (int a = 0; a < 16; ++a) v[a] = ci16_to_f2<TUNE_I2FP>(*reinterpret_cast<const unsigned int*>(st + off0 + (unsigned)a * 1024u));
+    if (w != nullptr) {
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+            const float wa = w[WS * a];
+            v[a].x *= wa;
+            v[a].y *= wa;
+        }
+    }
+    dft16_layer1(v);
+}
 SPX_HD void big2_dft_store(float2* v, int tid, float2* X) {
     using G = Stft2Geom<4096>;
     dft16_fma_layer2(v);

@@ -201,9 +201,11 @@ extern "C" int spx_emul_stft(int nfft, int in_fmt, int tw_mode, const void* in, 
 }
 
 // ------------------------------------------------------------------ K2v2: single-kernel 65536-point STFT, role by role
-template <bool ACC, int TUNE>
-static int emul_big2(const float2* in, long long n_samples, int hop, const float* win, float db_eps, float vmin, float vmax,
+template <bool ACC, int TUNE, int FMT = FMT_CF32>
+static int emul_big2(const void* in_any, long long n_samples, int hop, const float* win, float db_eps, float vmin, float vmax,
                      unsigned char* wf_rows, double* welch_acc, float* maxhold) {
+    const float2* in = reinterpret_cast<const float2*>(in_any);
+    const unsigned int* in16 = reinterpret_cast<const unsigned int*>(in_any);   // one ci16 sample = 4 bytes
     constexpr int N = BIG2_N;
     using G = Stft2Geom<4096>;
     const long long F = n_samples < N ? 0 : (n_samples - N) / hop + 1;
@@ -231,13 +233,23 @@ static int emul_big2(const float2* in, long long n_samples, int hop, const float
     const float pw_min = db_eps * db_eps * 1099511627776.0f;
     for (long long f = 0; f < F; ++f) {
         const float2* x = in + f * hop;
+        const unsigned int* x16 = in16 + f * hop;
         for (int g = 0; g < 16; ++g) {   // role A of every column tile
-            for (int n1 = 0; n1 < 256; ++n1)      // what the swizzled TMA box {128 B, 256 rows} leaves in shared memory
-                for (int ch = 0; ch < 8; ++ch) memcpy(&stage[swz128((unsigned)(128 * n1 + 16 * ch))], x + 256 * n1 + 16 * g + 2 * ch, 16);
+            for (int n1 = 0; n1 < 256; ++n1) {    // what the swizzled TMA box leaves in shared memory: {128 B, 256 rows} / ci16: {64 B, 256 rows}
+                if (FMT == FMT_CF32)
+                    for (int ch = 0; ch < 8; ++ch) memcpy(&stage[swz128((unsigned)(128 * n1 + 16 * ch))], x + 256 * n1 + 16 * g + 2 * ch, 16);
+                else
+                    for (int ch = 0; ch < 4; ++ch) memcpy(&stage[swz64((unsigned)(64 * n1 + 16 * ch))], x16 + 256 * n1 + 16 * g + 4 * ch, 16);
+            }
             for (int tid = 0; tid < 256; ++tid) {
                 float w[16];
                 if (win) for (int a = 0; a < 16; ++a) w[a] = win[big2_sample_of(g, a, tid)];
-                big2_phase_a<TUNE, 1>(&v[(size_t)tid * 16], tid, stage.data(), win ? w : nullptr, X.data());
+                if (FMT == FMT_CF32) {
+                    big2_phase_a<TUNE, 1>(&v[(size_t)tid * 16], tid, stage.data(), win ? w : nullptr, X.data());
+                } else {
+                    big2_load_tile_ci16<1>(&v[(size_t)tid * 16], tid, stage.data(), win ? w : nullptr);
+                    big2_dft_store(&v[(size_t)tid * 16], tid, X.data());
+                }
             }
             for (int tid = 0; tid < 256; ++tid) k2_phase_b1<4096, TUNE>(&v[(size_t)tid * 16], tid, X.data(), twr[tid]);
             for (int tid = 0; tid < 256; ++tid)
@@ -269,11 +281,18 @@ static int emul_big2(const float2* in, long long n_samples, int hop, const float
 extern "C" int spx_emul_big2(const void* in, long long n_samples, int hop, const float* win, float db_eps, float vmin, float vmax,
                              int tune, unsigned char* wf_rows, double* welch_acc, float* maxhold) {
     const bool acc = welch_acc != nullptr || maxhold != nullptr;
-    const float2* x = reinterpret_cast<const float2*>(in);
+    const void* x = in;
     if (tune) return acc ? emul_big2<true, TUNE_FMADFT | TUNE_QFMA>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold)
                          : emul_big2<false, TUNE_FMADFT | TUNE_QFMA>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold);
     return acc ? emul_big2<true, TUNE_FMADFT>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold)
                : emul_big2<false, TUNE_FMADFT>(x, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold);
+}
+
+extern "C" int spx_emul_big2_ci16(const void* in, long long n_samples, int hop, const float* win, float db_eps, float vmin, float vmax,
+                                  unsigned char* wf_rows, double* welch_acc, float* maxhold) {
+    const bool acc = welch_acc != nullptr || maxhold != nullptr;
+    return acc ? emul_big2<true, TUNE_FMADFT | TUNE_QFMA, FMT_CI16>(in, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold)
+               : emul_big2<false, TUNE_FMADFT | TUNE_QFMA, FMT_CI16>(in, n_samples, hop, win, db_eps, vmin, vmax, wf_rows, welch_acc, maxhold);
 }
 
 // plan introspection for the tests

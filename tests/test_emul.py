@@ -254,3 +254,25 @@ def test_emul_big2_roles(emul, tune):
     mh[:] = 0
     assert emul.spx_emul_big2(_p(tone), n, n, None, 1e-12, vmin, vmax, tune, None, None, _p(mh)) == 0
     assert int(np.argmax(mh)) == (k + n // 2) % n and abs(mh.max() / float(n) ** 2 - 1) < 1e-5
+
+
+def test_emul_big2_ci16_column_tiles(emul):
+    """K2v2 with int16 input: the {64 B x 256 rows} tile under CU_TENSOR_MAP_SWIZZLE_64B, int16 -> float, window * scale, then
+    the same roles as cf32 -- against the float64 oracle on three overlapped 65536-point frames (SigMF scale 2^-15)."""
+    n, hop = 65536, 32768
+    emul.spx_emul_big2_ci16.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p] + [C.c_float] * 3 + [C.c_void_p] * 3
+    L = n + 2 * hop + 100
+    raw = sref.to_ci16(sref.synth_iq(L, seed=66, tone_cycles_per_sample=20000.37 / 65536))
+    scale = 2.0 ** -15
+    w32 = (sref.window("hann", n) * scale).astype(np.float32)
+    F = sref.frame_count(L, n, hop)
+    wf = np.zeros((F, n), np.uint8)
+    welch = np.zeros(n, np.float64)
+    mh = np.zeros(n, np.float32)
+    vmin, vmax = -80.0, 40.0
+    assert emul.spx_emul_big2_ci16(_p(raw), L, hop, _p(w32), 1e-12, vmin, vmax, _p(wf), _p(welch), _p(mh)) == 0
+    X = sref.shift_bins(sref.stft(sref.unpack_ci16(raw, scale), n, hop, "hann"))
+    P = X.real**2 + X.imag**2
+    parity.check_u8(wf, sref.amplitude_db(X), vmin, vmax, what="K2v2 ci16 u8")
+    parity.check_power(welch, P.sum(axis=0), what="K2v2 ci16 welch")
+    parity.check_power(mh, P.max(axis=0), what="K2v2 ci16 maxhold")

@@ -423,6 +423,37 @@ def test_k2v2_single_kernel_65536(sp, hop, frames, kind, outs):
     pl.close(); old.close()
 
 
+@pytest.mark.parametrize("hop,frames,kind,scale", [(32768, 3, "hann", 1.0), (32768, 41, "blackman", 2.0**-15), (65536, 20, "rect", 1.0),
+                                                   (16384, 70, "hann", 2.0**-11), (256, 25, "rect", 2.0**-15)])
+def test_k2v2_int16_input(sp, hop, frames, kind, scale):
+    """K2v2 on int16 I/Q (column tiles of 64 B under the 64-byte TMA swizzle, int16 -> float and window * scale fused on load):
+    oracle parity on the first and last frames, agreement with the two-kernel path (variant 1) on every row."""
+    from sdr_iq_visualizer_b200 import _native as nat
+    n = 65536
+    L = n + hop * (frames - 1) + 77
+    raw = sref.to_ci16(sref.synth_iq(L, seed=frames + hop + 1, tone_cycles_per_sample=20000.37 / 65536))
+    db_shift = 20.0 * np.log10(scale * 1024.0)
+    vmin, vmax = -20.0 + db_shift, 110.0 + db_shift
+    kw = dict(wf_rows=True, welch=True, maxhold=True, vmin=vmin, vmax=vmax)
+    pl = sp.SpectralPlan(n, hop, kind, nat.FMT_CI16, in_scale=scale)
+    old = sp.SpectralPlan(n, hop, kind, nat.FMT_CI16, in_scale=scale, variant=1)
+    r, r0 = pl.stft(raw, **kw), old.stft(raw, **kw)
+    assert r.n_frames == r0.n_frames == frames
+    sel = sorted(set(range(min(frames, 3))) | set(range(max(0, frames - 2), frames)))
+    xc = sref.unpack_ci16(raw, scale)
+    X = np.stack([sref.shift_bins(sref.stft(xc[f * hop: f * hop + n], n, n, kind))[0] for f in sel])
+    parity.check_u8(r.wf_rows[sel], sref.amplitude_db(X), vmin, vmax, what=f"K2v2 ci16 u8 F={frames}")
+    assert np.abs(r.wf_rows.astype(np.int16) - r0.wf_rows.astype(np.int16)).max() <= 1
+    assert (r.wf_rows != r0.wf_rows).mean() < 2e-3
+    parity.check_power(r.welch_acc[0], r0.welch_acc[0], what="K2v2 ci16 welch vs two-kernel path", rel_tol=1.5e-4)
+    parity.check_power(r.maxhold[0], r0.maxhold[0], what="K2v2 ci16 maxhold vs two-kernel path", rel_tol=1.5e-4)
+    if frames <= 3:
+        P = X.real**2 + X.imag**2
+        parity.check_power(r.welch_acc[0], P.sum(axis=0), what="K2v2 ci16 welch")
+        parity.check_power(r.maxhold[0], P.max(axis=0), what="K2v2 ci16 maxhold")
+    pl.close(); old.close()
+
+
 @pytest.mark.parametrize("nfft,hop,fmt,L", [(4096, 1024, 1, 300_000), (65536, 32768, 0, 1 << 21)])
 def test_peer_output_pipeline_matches_direct_outputs(sp, monkeypatch, nfft, hop, fmt, L):
     """peer_outputs=True (multi-GPU capture shards): accumulators reduced with system-scope atomics, uint8 rows
