@@ -32,6 +32,13 @@ int launch_stft2(StftLaunch& L) {
         int rc = SPX_OK;
         if (launch_stft2_strip<2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L, &rc)) return rc;
     }
+    if (L.variant == 0 && L.nfft == 4096 && L.in_fmt == FMT_CF32 && L.p.hop >= 4096) {
+        // measured (profiles/r02_l2_prefetch_sweep.txt): the L2 prefetch of the next frame is +5 % here (one 32 KB frame in flight
+        // per CTA, all of it from HBM), neutral for int16, -1 % with overlap, -3 % for N = 2048 / 1024 (2 / 4 frames in flight per CTA)
+        const bool acc = L.p.welch_acc != nullptr || L.p.maxhold != nullptr;
+        constexpr int T = TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA | TUNE_L2PF;
+        return acc ? launch_stft2_inst<4096, FMT_CF32, true, 2, T>(L) : launch_stft2_inst<4096, FMT_CF32, false, 2, T>(L);
+    }
     if (L.variant == 22 || L.variant == 0) {   // default: FMA-form DFTs + uint8 index on the FMA / ALU pipes instead of F2I (XU)
         switch (L.nfft) {
             case 1024: return launch_stft2_n<1024, 2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L);

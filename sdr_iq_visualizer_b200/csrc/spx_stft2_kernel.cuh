@@ -89,13 +89,15 @@ __global__ void __launch_bounds__(256, OCC) stft2_kernel(const StftParams p, con
         else nxt.seek(p, cur.chunk + n_workers);
         float2* X = parity ? X1 : X0;
 
-        // Non-overlapping frames come straight from HBM, and the tensor copy of the next frame is only issued after this
-        // frame's barrier -- less than half a frame time to hide an HBM access.  Ask L2 for a later frame now: its copy,
-        // issued right after this frame's barrier, then has an L2 hit's latency (headline shape 0.745 -> 0.78 of HBM; overlapping
-        // frames are L2 hits already and lose 1 % to the extra requests: the launcher decides, see launch_stft2_inst).
-        if (p.l2_prefetch > 0 && tid == 0 && cur.fi + p.l2_prefetch < cur.nf) {
-            const char* src = reinterpret_cast<const char*>(p.in) + (cur.sample0(p) + (long long)p.l2_prefetch * p.hop) * ELT;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(C::FRAME_BYTES) : "memory");
+        // TUNE_L2PF (the launcher picks it for cf32, N = 4096, hop >= N).  Non-overlapping frames come straight from HBM, and the
+        // tensor copy of the next frame is only issued after this frame's barrier -- less than half a frame time to hide an HBM
+        // access.  Ask L2 for the next frame now: its copy then has an L2 hit's latency (headline shape 0.745 -> 0.78 of HBM).
+        // A compile-time switch: as a run-time branch it cost the overlapped int16 kernel 5 registers and 1.4 %.
+        if constexpr ((TUNE & TUNE_L2PF) != 0) {
+            if (tid == 0 && cur.fi + 1 < cur.nf) {
+                const char* src = reinterpret_cast<const char*>(p.in) + (cur.sample0(p) + (long long)p.hop) * ELT;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(C::FRAME_BYTES) : "memory");
+            }
         }
         mbar_wait(bar_u32, parity);
         k2_phase_a<N, FMT, TUNE>(v, tid, stage, wtab, X);
@@ -270,11 +272,6 @@ int launch_stft2_inst(StftLaunch& L) {
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return spx_set_error(SPX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    // L2 prefetch of the next frame: measured (profiles/r02_l2_prefetch_sweep.txt) +5 % on cf32 N = 4096 without overlap (one
-    // 32 KB frame in flight per CTA), neutral for ci16, -3 % for N = 2048 / 1024 (2 / 4 frames in flight per CTA already);
-    // SPX_L2PF_DIST overrides the distance for every hop >= N shape (experiments)
-    static const int l2pf_env = getenv("SPX_L2PF_DIST") ? atoi(getenv("SPX_L2PF_DIST")) : -1;
-    L.p.l2_prefetch = L.p.hop < N ? 0 : (l2pf_env >= 0 ? l2pf_env : ((N == 4096 && FMT == FMT_CF32) ? 1 : 0));
     kern<<<(unsigned)grid, C::THREADS, C::SMEM, L.stream>>>(L.p, tmap);
     SPX_CUDA(cudaGetLastError());
     return SPX_OK;

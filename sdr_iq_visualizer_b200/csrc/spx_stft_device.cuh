@@ -35,7 +35,6 @@ struct StftParams {
     int frames_per_chunk;        // accumulator flush granularity (<= 256)
     int chunks_per_stream;
     long long total_chunks;
-    int l2_prefetch;             // K1v2: frames ahead whose new samples are requested into L2 (0 = off; set by the launcher when hop >= N)
 };
 
 // ------------------------------------------------------------------ device/host primitives
@@ -50,7 +49,7 @@ SPX_HD float2 ld_stream_cf32(const float2* p) {
 }
 // kernel tuning bits (template parameter TUNE).  FMADFT: radix-16 DFTs in FMA form (dft16_fma).  QFMA: the uint8 colormap
 // index is produced on the FMA / ALU pipes (saturating FMA, min, round-down FMA onto 2^23) instead of F2I on the XU pipe.
-enum { TUNE_I2FP = 1, TUNE_FMADFT = 2, TUNE_QFMA = 4 };
+enum { TUNE_I2FP = 1, TUNE_FMADFT = 2, TUNE_QFMA = 4, TUNE_L2PF = 8 };
 
 // packed int16 I,Q -> float2.  Default: two I2F.S16 (XU pipe, 16 lanes/clk/SM).  TUNE_I2FP: sign-extend with
 // PRMT and convert with I2FP.F32.S32 (ALU pipe) -- exact either way (|v| <= 2^15 fits a float).

@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""hop >= N shapes of K1v2 with the L2 prefetch distance given by SPX_L2PF_DIST (0 = off): python tools/sweep_l2pf.py"""
+"""hop >= N shapes of K1v2.  profiles/r02_l2_prefetch_sweep.txt was produced with a run-time knob (SPX_L2PF_DIST = frames ahead,
+0 = off) that has since been replaced by the compile-time switch TUNE_L2PF (distance 1, cf32 N = 4096 only: as a run-time branch
+it cost the overlapped int16 kernel 1.4 %); today this script just times the shapes with the default kernels."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import kernel_sweep as ks
