@@ -20,6 +20,27 @@ tmap_encode_fn tmap_encoder() {
     return fn;
 }
 
+// Default kernels with the set of row outputs fixed at compile time (uint8 rows only / f32 dB rows only / accumulators only /
+// read from the parameters): as run-time branches in the frame loop the unused outputs cost registers and 1 - 2 % (measured on
+// config 2: 106.2 -> 107.8 GS/s).
+template <int N, int FMT, int TUNE>
+static int launch_acc(StftLaunch& L, bool acc) {
+    return acc ? launch_stft2_inst<N, FMT, true, 2, TUNE>(L) : launch_stft2_inst<N, FMT, false, 2, TUNE>(L);
+}
+template <int N, int FMT, int TUNE>
+static int launch_outs(StftLaunch& L) {
+    const bool acc = L.p.welch_acc != nullptr || L.p.maxhold != nullptr;
+    const bool wf = L.p.wf_rows != nullptr, db = L.p.db_rows != nullptr, spec = L.p.spec_rows != nullptr;
+    if (wf && !db && !spec) return launch_acc<N, FMT, TUNE | TUNE_ONLY_U8>(L, acc);
+    if (db && !wf && !spec) return launch_acc<N, FMT, TUNE | TUNE_ONLY_DB>(L, acc);
+    if (acc && !wf && !db && !spec) return launch_stft2_inst<N, FMT, true, 2, TUNE | TUNE_NO_ROWS>(L);
+    return launch_acc<N, FMT, TUNE>(L, acc);
+}
+template <int N, int TUNE>
+static int launch_fmt_outs(StftLaunch& L) {
+    return L.in_fmt == FMT_CF32 ? launch_outs<N, FMT_CF32, TUNE>(L) : launch_outs<N, FMT_CI16, TUNE>(L);
+}
+
 int launch_stft2(StftLaunch& L) {
     if (L.variant == 23) {   // strip staging of overlapping frames (experiment; N = 4096, hop = N/2 or N/4), else the default
         int rc = SPX_OK;
@@ -32,12 +53,17 @@ int launch_stft2(StftLaunch& L) {
         int rc = SPX_OK;
         if (launch_stft2_strip<2, TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA>(L, &rc)) return rc;
     }
-    if (L.variant == 0 && L.nfft == 4096 && L.in_fmt == FMT_CF32 && L.p.hop >= 4096) {
-        // measured (profiles/r02_l2_prefetch_sweep.txt): the L2 prefetch of the next frame is +5 % here (one 32 KB frame in flight
-        // per CTA, all of it from HBM), neutral for int16, -1 % with overlap, -3 % for N = 2048 / 1024 (2 / 4 frames in flight per CTA)
-        const bool acc = L.p.welch_acc != nullptr || L.p.maxhold != nullptr;
-        constexpr int T = TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA | TUNE_L2PF;
-        return acc ? launch_stft2_inst<4096, FMT_CF32, true, 2, T>(L) : launch_stft2_inst<4096, FMT_CF32, false, 2, T>(L);
+    if (L.variant == 0) {
+        constexpr int T0 = TUNE_I2FP | TUNE_FMADFT | TUNE_QFMA;
+        // L2 prefetch of the next frame (compile-time as well): cf32, N = 4096 without overlap only (+ 5 %,
+        // profiles/r02_l2_prefetch_sweep.txt; neutral for int16, - 1 % with overlap, - 3 % for N = 2048 / 1024 with their 2 / 4
+        // frames in flight per CTA)
+        if (L.nfft == 4096 && L.in_fmt == FMT_CF32 && L.p.hop >= 4096) return launch_outs<4096, FMT_CF32, T0 | TUNE_L2PF>(L);
+        switch (L.nfft) {
+            case 1024: return launch_fmt_outs<1024, T0>(L);
+            case 2048: return launch_fmt_outs<2048, T0>(L);
+            case 4096: return launch_fmt_outs<4096, T0>(L);
+        }
     }
     if (L.variant == 22 || L.variant == 0) {   // default: FMA-form DFTs + uint8 index on the FMA / ALU pipes instead of F2I (XU)
         switch (L.nfft) {

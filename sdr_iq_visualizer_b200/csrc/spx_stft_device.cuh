@@ -49,7 +49,10 @@ SPX_HD float2 ld_stream_cf32(const float2* p) {
 }
 // kernel tuning bits (template parameter TUNE).  FMADFT: radix-16 DFTs in FMA form (dft16_fma).  QFMA: the uint8 colormap
 // index is produced on the FMA / ALU pipes (saturating FMA, min, round-down FMA onto 2^23) instead of F2I on the XU pipe.
-enum { TUNE_I2FP = 1, TUNE_FMADFT = 2, TUNE_QFMA = 4, TUNE_L2PF = 8 };
+enum { TUNE_I2FP = 1, TUNE_FMADFT = 2, TUNE_QFMA = 4, TUNE_L2PF = 8,
+       TUNE_ONLY_U8 = 16,    // the launch writes uint8 rows (and accumulators) only: the other row outputs are compiled out
+       TUNE_ONLY_DB = 32,    // ... f32 dB rows only
+       TUNE_NO_ROWS = 64 };  // ... no rows at all (Welch / max-hold accumulators only)
 
 // packed int16 I,Q -> float2.  Default: two I2F.S16 (XU pipe, 16 lanes/clk/SM).  TUNE_I2FP: sign-extend with
 // PRMT and convert with I2FP.F32.S32 (ALU pipe) -- exact either way (|v| <= 2^15 fits a float).
@@ -327,7 +330,12 @@ SPX_HD constexpr int shift_off(int t) {
 template <int N, bool ACC, int TUNE = 0>
 SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, StftAcc<ACC>& acc) {
     constexpr int S = plan_passes(N) - 1, R = plan_radix(N, S), NB = 16 / R, T = N / 16;
-    if (p.spec_rows) {
+    // which row outputs exist: read from the parameters, or fixed at compile time for the launcher's specialised instantiations
+    constexpr bool FIXED = (TUNE & (TUNE_ONLY_U8 | TUNE_ONLY_DB | TUNE_NO_ROWS)) != 0;
+    const bool want_spec = FIXED ? false : p.spec_rows != nullptr;
+    const bool want_db = FIXED ? (TUNE & TUNE_ONLY_DB) != 0 : p.db_rows != nullptr;
+    const bool want_wf = FIXED ? (TUNE & TUNE_ONLY_U8) != 0 : p.wf_rows != nullptr;
+    if (want_spec) {
         float2* sp = p.spec_rows + row * N + tid;
 #pragma unroll
         for (int u = 0; u < NB; ++u)
@@ -343,7 +351,7 @@ SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, Stf
             acc.mx[i] = fmaxf(acc.mx[i], v[i].x);
         }
     }
-    if (p.db_rows || p.wf_rows) {
+    if (want_db || want_wf) {
         // smallest of this thread's 16 powers decides (one branch) whether the eps term can matter
         float m01 = fminf(v[0].x, v[1].x), m23 = fminf(v[2].x, v[3].x), m45 = fminf(v[4].x, v[5].x);
         float m67 = fminf(v[6].x, v[7].x), m89 = fminf(v[8].x, v[9].x), mab = fminf(v[10].x, v[11].x);
@@ -357,14 +365,14 @@ SPX_HD void epilogue(float2* v, int tid, const StftParams& p, long long row, Stf
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i].y = 2.0f * fast_log2(fast_sqrt(v[i].x) + p.db_eps);
         }
-        if (p.db_rows) {
+        if (want_db) {
             float* db = p.db_rows + row * N + tid;
 #pragma unroll
             for (int u = 0; u < NB; ++u)
 #pragma unroll
                 for (int t = 0; t < R; ++t) db[shift_off<N>(t) + T * u] = (0.5f * SPX_DB_PER_LOG2) * v[u * R + t].y;
         }
-        if (p.wf_rows) {
+        if (want_wf) {
             unsigned char* wf = p.wf_rows + row * N + tid;
             if constexpr ((TUNE & TUNE_QFMA) != 0) {
                 const float qa = p.q_a * 0.00390625f, qb = p.q_b * 0.00390625f;
